@@ -1,0 +1,99 @@
+"""CPU tests: the plain-C oracle against (a) the committed golden vectors produced by the compiled
+reference (tests/golden/make_golden.py) and (b) the compiled reference itself where it is available."""
+import numpy as np
+import pytest
+
+from conftest import CASES, GOLDEN, load_case
+
+DIMS = (1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 23, 24, 31, 32, 40, 48, 100, 128, 200, 203, 512)
+
+
+def bits(x):
+    return np.ascontiguousarray(x, np.float32).view(np.uint32)
+
+
+def test_distance_golden(oracle):
+    z = np.load(GOLDEN + "/distance.npz")
+    for d in DIMS:
+        a, b = z[f"a_{d}"].astype(np.float32), z[f"b_{d}"].astype(np.float32)
+        assert (bits(oracle.distance_batch(0, a, b)) == bits(z[f"l2_{d}"])).all(), d
+        assert (bits(oracle.distance_batch(1, a, b)) == bits(z[f"ip_{d}"])).all(), d
+        # COSINE uses DistanceInnerProduct (src/index.cpp:14-17)
+        assert (bits(oracle.distance_batch(4, a, b)) == bits(z[f"ip_{d}"])).all(), d
+
+
+def test_pool_golden(oracle):
+    z = np.load(GOLDEN + "/pool.npz")
+    for i in range(5):
+        oi, od, of, pop = oracle.pool_script(int(z[f"cap_{i}"]), z[f"kind_{i}"], z[f"ids_{i}"], z[f"dists_{i}"])
+        assert (oi == z[f"out_ids_{i}"]).all() and (bits(od) == bits(z[f"out_dists_{i}"])).all()
+        assert (of == z[f"out_flags_{i}"]).all() and (pop == z[f"pop_{i}"]).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_search_golden(oracle, name):
+    c = load_case(name)
+    for L in c["Ls"]:
+        r = oracle.search(c["base"], c["offsets"], c["adj"], c["ep"], c["test"], 10, int(L), metric=c["metric"])
+        assert r["rc"] == 0
+        assert (r["ids"] == c[f"ids_{L}"]).all()
+        assert (bits(r["dists"]) == bits(c[f"dists_{L}"])).all()
+        assert (r["cmps"] == c[f"cmps_{L}"]).all() and (r["hops"] == c[f"hops_{L}"]).all()
+
+
+def test_search_not_enough_results(oracle):
+    # a 3-node graph cannot return k=10 (src/index_bipartite.cpp:2408-2412)
+    base = np.eye(3, 8, dtype=np.float32)
+    off = np.array([0, 2, 3, 4], np.uint64)
+    adj = np.array([1, 2, 0, 0], np.uint32)
+    r = oracle.search(base, off, adj, 0, base[:1], 10, 16, metric=1)
+    assert r["rc"] == 2
+    r = oracle.search(base, off, adj, 0, base[:1], 3, 16, metric=1)
+    assert r["rc"] == 0 and sorted(r["ids"][0]) == [0, 1, 2] and r["cmps"][0] == 3  # ep re-scored once
+
+
+@pytest.mark.parametrize("metric", (0, 1))
+def test_knn_matches_fp64(oracle, metric):
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((3000, 40)).astype(np.float32)
+    q = rng.standard_normal((50, 40)).astype(np.float32)
+    ids, dists, _ = oracle.exact_knn(base, q, 20, metric=metric, part_size=1000)
+    ids1, dists1, _ = oracle.exact_knn(base, q, 20, metric=metric)  # single part: same answer
+    assert (ids == ids1).all() and (bits(dists) == bits(dists1)).all()
+    s = q.astype(np.float64) @ base.astype(np.float64).T
+    if metric == 0:
+        s = (q.astype(np.float64) ** 2).sum(1)[:, None] + (base.astype(np.float64) ** 2).sum(1)[None] - 2 * s
+        want = np.sort(s, axis=1)[:, :20]
+    else:
+        want = -np.sort(-s, axis=1)[:, :20]   # stored as +ip, descending (compute_groundtruth.cpp:438-441)
+    assert np.allclose(dists, want, rtol=1e-5, atol=1e-5)
+    got_set = [set(r) for r in ids]
+    ref_ids = np.argsort(s if metric == 0 else -s, axis=1)[:, :20]
+    assert np.mean([len(g & set(r)) / 20 for g, r in zip(got_set, ref_ids)]) > 0.999
+
+
+def test_recall(oracle):
+    gt = np.array([[1, 2, 3, 9], [4, 5, 6, 9]], np.uint32)
+    res = np.array([[3, 1, 7], [8, 8, 8]], np.uint32)
+    assert oracle.recall(res, gt, 3) == pytest.approx(2 / 6)
+
+
+# ---- live differential checks against the compiled reference (only where oracle/_ref exists) ----
+def test_distance_vs_ref(oracle, ref):
+    rng = np.random.default_rng(9)
+    for d in (8, 24, 200, 203, 512, 960):
+        a = (rng.standard_normal((4000, d)) * 5).astype(np.float32)
+        b = rng.standard_normal((4000, d)).astype(np.float32)
+        for m in (0, 1):
+            assert (bits(oracle.distance_batch(m, a, b)) == bits(ref.distance_batch(m, a, b))).all()
+
+
+def test_pool_vs_ref(oracle, ref):
+    rng = np.random.default_rng(10)
+    for cap in (1, 2, 7, 64, 500):
+        nops = 4000
+        kind = (rng.random(nops) < 0.2).astype(np.uint8)
+        ids = rng.integers(0, 900, nops).astype(np.uint32)
+        dists = np.round(rng.standard_normal(nops), 1).astype(np.float32)
+        a, b = oracle.pool_script(cap, kind, ids, dists), ref.pool_script(cap, kind, ids, dists)
+        assert all((x == y).all() for x, y in zip(a, b))
