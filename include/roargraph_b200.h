@@ -1,0 +1,112 @@
+/*
+ * roargraph_b200.h - C ABI of the B200-native RoarGraph hot path (libroargraph_b200.so).
+ *
+ * The reference (matchyc/mysteryann) has no FFI: its boundary is the C++ class
+ * efanna2e::IndexBipartite (include/index_bipartite.h:23-171) called from the CLI drivers
+ * tests/test_search_roargraph.cpp and tests/test_build_roargraph.cpp, plus the DiskANN tool
+ * thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp that produces the learn->base kNN file.
+ * This header is the thin C layer the host C++ (mysteryann_b200/host/, same class and method
+ * names as the reference) calls into; every entry point cites the reference code it replaces.
+ * Paths below are relative to the reference repository root.
+ *
+ * Conventions: plain C types only; all sizes in elements unless stated; "host" pointers are
+ * ordinary (pageable or pinned) CPU memory, "device" pointers are CUDA device memory on the
+ * index's device; every function returns an rg_status and records a message retrievable with
+ * rg_last_error_string() (thread local).  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with RG_ERR_NO_DEVICE.
+ */
+#ifndef ROARGRAPH_B200_H
+#define ROARGRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_API __attribute__((visibility("default")))
+
+typedef int rg_status;
+enum {
+    RG_OK = 0,
+    RG_ERR_INVALID_ARGUMENT = 1,
+    RG_ERR_CUDA = 2,
+    RG_ERR_NOT_ENOUGH_RESULTS = 3, /* src/index_bipartite.cpp:2408-2412 "not enough results: .., expected: .." */
+    RG_ERR_OUT_OF_MEMORY = 4,
+    RG_ERR_NO_DEVICE = 5,
+    RG_ERR_INTERNAL = 6,
+    RG_ERR_IO = 7
+};
+
+/* efanna2e::Metric, include/efanna2e/distance.h:15.  COSINE searches with the inner-product
+ * distance on L2-normalised rows exactly like the reference (src/index.cpp:14-17;
+ * normalisation is done by the caller: src/index_bipartite.cpp:2675-2680, tests/test_search_roargraph.cpp:167-172). */
+enum { RG_METRIC_L2 = 0, RG_METRIC_INNER_PRODUCT = 1, RG_METRIC_COSINE = 4 };
+
+typedef struct rg_index rg_index; /* device-resident base vectors + projection graph + entry point */
+
+RG_API const char *rg_last_error_string(void);
+RG_API const char *rg_version_string(void);
+RG_API int rg_device_count(void);
+
+/* ---- index ------------------------------------------------------------------------------------
+ * Replaces IndexBipartite::LoadVectorData + LoadProjectionGraph (src/index_bipartite.cpp:2661-2692,
+ * 2097-2117): uploads the base rows and the adjacency (CSR: adj_offsets[n+1], adj[adj_offsets[n]])
+ * to `device`.  `dim` is the padded row length (multiple of 8, include/efanna2e/util.h:37-75).
+ * base may be a host pointer (copied) or, with base_on_device != 0, a device pointer that is
+ * adopted WITHOUT copying and must outlive the index.  ep = projection_ep_. */
+RG_API rg_status rg_index_create(rg_index **out, const float *base, uint64_t n, uint32_t dim, int metric,
+                                 const uint64_t *adj_offsets, const uint32_t *adj, uint32_t ep, int device,
+                                 int base_on_device);
+RG_API rg_status rg_index_destroy(rg_index *index);
+RG_API rg_status rg_index_info(const rg_index *index, uint64_t *n, uint32_t *dim, int *metric, uint32_t *ep,
+                               uint32_t *max_degree, int *device);
+
+/* ---- search -----------------------------------------------------------------------------------
+ * Replaces the timed loop of tests/test_search_roargraph.cpp:203-209, i.e. nq calls of
+ * IndexBipartite::SearchRoarGraph (src/index_bipartite.cpp:2311-2420) with L_pq = L:
+ * ids[nq*k], dists[nq*k] (IP: negated dot; L2: squared distance), cmps[nq], hops[nq]
+ * (cmps/hops may be NULL).  Results are bit-identical to the reference's.
+ * Host variant: queries/results are host buffers; H2D, kernels and D2H happen inside the call.
+ * Returns RG_ERR_NOT_ENOUGH_RESULTS if any query ends with fewer than k pool entries (its ids
+ * are filled with 0xFFFFFFFF), like the reference's std::runtime_error. */
+RG_API rg_status rg_search_batch(rg_index *index, const float *queries, uint64_t nq, uint32_t k, uint32_t L,
+                                 uint32_t *ids, float *dists, uint32_t *cmps, uint32_t *hops);
+/* Device variant: all buffers are device memory, work is enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream) and the call returns without synchronising.  d_status (may be NULL)
+ * receives 2 x u32: {#queries with fewer than k results, #queries whose visited set overflowed
+ * every fallback (must be 0)}. */
+RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries, uint64_t nq, uint32_t k,
+                                        uint32_t L, uint32_t *d_ids, float *d_dists, uint32_t *d_cmps,
+                                        uint32_t *d_hops, uint32_t *d_status, void *cuda_stream);
+/* Tuning knobs (0 = automatic): see DESIGN.md "K1".  gather: 0 auto, 1 cp.async (LDGSTS),
+ * 2 TMA bulk copy (cp.async.bulk + mbarrier). */
+RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_cta, int ctas_per_sm,
+                                     int stage_rows, int hash_log2);
+/* Number of kernel launches issued by this library on behalf of `index` so far. */
+RG_API uint64_t rg_index_launch_count(const rg_index *index);
+
+/* ---- exact kNN (build time) -------------------------------------------------------------------
+ * Replaces exact_knn + the per-part merge of compute_groundtruth.cpp:126-248, 396-448 for one base
+ * shard: for each of nq queries the K base rows with the smallest score (-<p,q> for
+ * RG_METRIC_INNER_PRODUCT, squared L2 otherwise), ascending by (score, id); ids are
+ * shard-local row + id_base; dists are written as +<p,q> for inner product
+ * (compute_groundtruth.cpp:438-441).  Host buffers. */
+RG_API rg_status rg_knn_exact(const float *base, uint64_t n, uint64_t id_base, const float *queries, uint64_t nq,
+                              uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists, int device);
+/* Device variant, asynchronous on cuda_stream. */
+RG_API rg_status rg_knn_exact_device(const float *d_base, uint64_t n, uint64_t id_base, const float *d_queries,
+                                     uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *d_ids,
+                                     float *d_dists, int device, void *cuda_stream);
+/* K4: merges G per-shard lists (each nq x K, ascending by (score,id), in the OUTPUT convention
+ * above) into the global top-K; replaces the concat + std::sort of compute_groundtruth.cpp:424-448.
+ * Device buffers: d_part_ids/d_part_dists are [G][nq][K]. */
+RG_API rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_part_dists, uint32_t G,
+                                     uint64_t nq, uint32_t K, int metric, uint32_t *d_ids, float *d_dists,
+                                     int device, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROARGRAPH_B200_H */

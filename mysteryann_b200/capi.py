@@ -1,0 +1,145 @@
+"""ctypes binding of the C ABI declared in include/roargraph_b200.h (libroargraph_b200.so).
+
+This is harness plumbing for tests/ and bench.py; the drop-in host layer is the C++ class
+efanna2e::IndexBipartite in mysteryann_b200/host/.  There is no CPU fallback: if the CUDA library is
+missing or no device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libroargraph_b200.so")
+
+RG_OK = 0
+RG_ERR_NOT_ENOUGH_RESULTS = 3
+RG_ERR_NO_DEVICE = 5
+METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
+
+SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
+           "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure",
+           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device"]
+
+_lib = None
+
+
+class RoarGraphError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RoarGraphError(-1, f"{LIB_PATH} is missing: run `python -m mysteryann_b200.build` "
+                                 "(the CUDA extension is required; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.rg_last_error_string.restype = C.c_char_p
+    L.rg_version_string.restype = C.c_char_p
+    L.rg_device_count.restype = i32
+    L.rg_index_create.restype = i32
+    L.rg_index_create.argtypes = [C.POINTER(vp), vp, u64, u32, i32, vp, vp, u32, i32, i32]
+    L.rg_index_destroy.restype = i32
+    L.rg_index_destroy.argtypes = [vp]
+    L.rg_index_info.restype = i32
+    L.rg_index_info.argtypes = [vp] + [vp] * 6
+    L.rg_search_batch.restype = i32
+    L.rg_search_batch.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp]
+    L.rg_search_batch_device.restype = i32
+    L.rg_search_batch_device.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp, vp, vp]
+    L.rg_search_configure.restype = i32
+    L.rg_search_configure.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.rg_index_launch_count.restype = u64
+    L.rg_index_launch_count.argtypes = [vp]
+    L.rg_knn_exact.restype = i32
+    L.rg_knn_exact.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, i32]
+    L.rg_knn_exact_device.restype = i32
+    L.rg_knn_exact_device.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, i32, vp]
+    L.rg_knn_merge_device.restype = i32
+    L.rg_knn_merge_device.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != RG_OK:
+        raise RoarGraphError(rc, (lib().rg_last_error_string() or b"").decode())
+
+
+def device_count() -> int:
+    return int(lib().rg_device_count())
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data
+
+
+class Index:
+    """Device-resident RoarGraph index (base rows + projection graph + entry point)."""
+
+    def __init__(self, base, offsets, adj, ep, metric=METRIC_IP, device=0):
+        """base: numpy float32 [n, dim] (copied to the device) or a CUDA torch tensor (adopted, kept alive)."""
+        L = lib()
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        adj = np.ascontiguousarray(adj, np.uint32)
+        self._keep = None
+        if isinstance(base, np.ndarray):
+            base = np.ascontiguousarray(base, np.float32)
+            n, dim = base.shape
+            ptr, on_dev = base.ctypes.data, 0
+        else:  # torch CUDA tensor
+            assert base.is_cuda and base.is_contiguous() and base.dtype.is_floating_point and base.element_size() == 4
+            n, dim = base.shape
+            ptr, on_dev = base.data_ptr(), 1
+            device = base.device.index or 0
+            self._keep = base
+        self.n, self.dim, self.metric, self.device, self.ep = int(n), int(dim), metric, device, int(ep)
+        h = C.c_void_p()
+        _check(L.rg_index_create(C.byref(h), ptr, n, dim, metric, _hp(offsets), _hp(adj), ep, device, on_dev))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rg_index_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def configure(self, gather=0, warps_per_cta=0, ctas_per_sm=0, stage_rows=0, hash_log2=0):
+        _check(lib().rg_search_configure(self._h, gather, warps_per_cta, ctas_per_sm, stage_rows, hash_log2))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().rg_index_launch_count(self._h))
+
+    def search(self, queries, k, L, want_stats=True):
+        """Host-buffer call (H2D + kernels + D2H inside).  queries: numpy float32 [nq, dim]."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, d = queries.shape
+        assert d == self.dim
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        cmps = np.empty(nq, np.uint32) if want_stats else None
+        hops = np.empty(nq, np.uint32) if want_stats else None
+        rc = lib().rg_search_batch(self._h, _hp(queries), nq, k, L, _hp(ids), _hp(dists), _hp(cmps), _hp(hops))
+        if rc not in (RG_OK, RG_ERR_NOT_ENOUGH_RESULTS):
+            _check(rc)
+        return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, rc=rc)
+
+    def search_raw(self, q_ptr, nq, k, L, ids_ptr, dists_ptr, cmps_ptr=None, hops_ptr=None):
+        """Host-buffer call on raw addresses (e.g. pinned torch tensors)."""
+        _check(lib().rg_search_batch(self._h, q_ptr, nq, k, L, ids_ptr, dists_ptr, cmps_ptr, hops_ptr))
+
+    def search_device(self, d_queries, k, L, d_ids, d_dists, d_cmps=None, d_hops=None, d_status=None, stream=None):
+        """Device-buffer call on CUDA torch tensors; asynchronous on `stream` (int handle or None)."""
+        nq = d_queries.shape[0]
+        p = lambda t: None if t is None else t.data_ptr()
+        _check(lib().rg_search_batch_device(self._h, p(d_queries), nq, k, L, p(d_ids), p(d_dists), p(d_cmps),
+                                            p(d_hops), p(d_status), stream))

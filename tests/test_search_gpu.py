@@ -1,0 +1,156 @@
+"""GPU parity tests of K1 (beam search) through the C ABI: bit-exact ids / dists / cmps / hops against
+(a) the golden vectors produced by the compiled reference and (b) the CPU oracle on seeded random graphs."""
+import numpy as np
+import pytest
+
+from conftest import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return np.ascontiguousarray(x, np.float32).view(np.uint32)
+
+
+def report(tag, got, want):
+    """assert equality with a useful message"""
+    for key in ("hops", "cmps", "ids"):
+        g, w = got[key], want[key]
+        if not (g == w).all():
+            bad = np.argwhere(g != w)
+            q = int(bad[0][0])
+            raise AssertionError(f"{tag}: {key} differs in {len(set(bad[:, 0]))} queries; first q={q}: got "
+                                 f"{got[key][q]} want {want[key][q]} | hops {got['hops'][q]}/{want['hops'][q]} "
+                                 f"cmps {got['cmps'][q]}/{want['cmps'][q]}")
+    gb, wb = bits(got["dists"]), bits(want["dists"])
+    if not (gb == wb).all():
+        bad = np.argwhere(gb != wb)
+        q, j = bad[0]
+        raise AssertionError(f"{tag}: dists differ at {len(bad)} places; first q={q} j={j}: "
+                             f"{got['dists'][q, j]!r} vs {want['dists'][q, j]!r}")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mysteryann_b200 import build, capi
+
+    build.build()
+    assert capi.device_count() > 0, "no CUDA device"
+    return capi
+
+
+@pytest.mark.parametrize("gather", (1, 2))
+@pytest.mark.parametrize("name", CASES)
+def test_golden(capi, name, gather):
+    c = load_case(name)
+    ix = capi.Index(c["base"], c["offsets"], c["adj"], c["ep"], metric=c["metric"])
+    ix.configure(gather=gather)
+    for L in c["Ls"]:
+        L = int(L)
+        got = ix.search(c["test"], 10, L)
+        assert got["rc"] == 0
+        want = {k: c[f"{k}_{L}"] for k in ("ids", "dists", "cmps", "hops")}
+        report(f"{name} L={L} gather={gather}", got, want)
+    ix.close()
+
+
+def random_graph(rng, n, dmin, dmax, zero_frac=0.0):
+    deg = rng.integers(dmin, dmax + 1, n)
+    if zero_frac:
+        deg[rng.random(n) < zero_frac] = 0
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=off[1:])
+    adj = rng.integers(0, n, int(off[-1])).astype(np.uint32)   # may contain duplicates and self loops
+    return off, adj
+
+
+@pytest.mark.parametrize("metric", (0, 1))
+@pytest.mark.parametrize("dim,dmin,dmax", [(200, 1, 70), (512, 8, 40), (64, 0, 95), (8, 3, 12), (104, 30, 130)])
+def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
+    rng = np.random.default_rng(dim * 7 + metric)
+    n, nq = 20000, 300
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, dmin, dmax, zero_frac=0.01)
+    ep = int(rng.integers(0, n))
+    if off[ep + 1] == off[ep]:
+        ep = int(np.argmax(np.diff(off)))
+    ix = capi.Index(base, off, adj, ep, metric=metric)
+    for gather in (1, 2):
+        ix.configure(gather=gather)
+        for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
+            want = oracle.search(base, off, adj, ep, q, k, L, metric=metric)
+            got = ix.search(q, k, L)
+            assert got["rc"] == want["rc"] == 0
+            report(f"dim={dim} metric={metric} gather={gather} L={L}", got, want)
+    ix.close()
+
+
+def test_visited_overflow_takes_exact_fallback(capi, oracle):
+    """A tiny shared-memory hash forces most queries through the global-table pass; results stay exact."""
+    rng = np.random.default_rng(5)
+    n, dim = 30000, 40
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((200, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 20, 60)
+    ix = capi.Index(base, off, adj, 3, metric=1)
+    ix.configure(hash_log2=8)
+    want = oracle.search(base, off, adj, 3, q, 10, 50, metric=1)
+    assert want["cmps"].max() > 256
+    report("overflow", ix.search(q, 10, 50), want)
+    ix.configure(hash_log2=16)   # > 15: the primary pass itself uses global-memory tables
+    report("global-primary", ix.search(q, 10, 50), want)
+    ix.close()
+
+
+def test_large_L_and_ties(capi, oracle):
+    """Large beam widths (pool in shared memory up to L=2000) and heavy distance ties (grid-valued vectors)."""
+    rng = np.random.default_rng(8)
+    n, dim = 8000, 16
+    base = rng.integers(-2, 3, (n, dim)).astype(np.float32)     # many exact ties, incl. duplicated rows
+    q = rng.integers(-2, 3, (100, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 10, 30)
+    for metric in (0, 1):
+        ix = capi.Index(base, off, adj, 1, metric=metric)
+        for L in (10, 100, 500, 2000):
+            want = oracle.search(base, off, adj, 1, q, 10, L, metric=metric)
+            report(f"ties metric={metric} L={L}", ix.search(q, 10, L), want)
+        ix.close()
+
+
+def test_not_enough_results(capi):
+    base = np.eye(3, 8, dtype=np.float32)
+    off = np.array([0, 2, 3, 4], np.uint64)
+    adj = np.array([1, 2, 0, 0], np.uint32)
+    ix = capi.Index(base, off, adj, 0, metric=1)
+    r = ix.search(base[:1], 10, 16)
+    assert r["rc"] == capi.RG_ERR_NOT_ENOUGH_RESULTS and (r["ids"] == 0xFFFFFFFF).all()
+    assert b"not enough results" in capi.lib().rg_last_error_string()
+    r = ix.search(base[:1], 3, 16)
+    assert r["rc"] == 0 and sorted(r["ids"][0]) == [0, 1, 2] and r["cmps"][0] == 3 and r["hops"][0] == 3
+    with pytest.raises(capi.RoarGraphError):   # k > L (tests/test_search_roargraph.cpp:192-195)
+        ix.search(base[:1], 10, 5)
+    ix.close()
+
+
+def test_device_api_and_empty_batch(capi, oracle):
+    import torch
+
+    c = load_case("ip_d200")
+    ix = capi.Index(torch.from_numpy(c["base"]).cuda(), c["offsets"], c["adj"], c["ep"], metric=1)
+    dq = torch.from_numpy(c["test"]).cuda()
+    nq, k, L = dq.shape[0], 10, 32
+    ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    dists = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    cmps = torch.empty(nq, dtype=torch.int32, device="cuda")
+    hops = torch.empty(nq, dtype=torch.int32, device="cuda")
+    status = torch.full((2,), 7, dtype=torch.int32, device="cuda")
+    ix.search_device(dq, k, L, ids, dists, cmps, hops, status, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = dict(ids=ids.cpu().numpy().view(np.uint32), dists=dists.cpu().numpy(),
+               cmps=cmps.cpu().numpy().view(np.uint32), hops=hops.cpu().numpy().view(np.uint32))
+    report("device api", got, {k_: c[f"{k_}_{L}"] for k_ in ("ids", "dists", "cmps", "hops")})
+    assert status.cpu().tolist() == [0, 0]
+    assert ix.launches >= 3
+    assert ix.search(np.zeros((0, 200), np.float32), 10, 32)["ids"].shape == (0, 10)
+    ix.close()
