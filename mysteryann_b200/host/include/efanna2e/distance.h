@@ -24,42 +24,75 @@ class Distance {
 };
 
 namespace detail {
-// kSquaredDiff = false: sum a[i]*b[i];  true: sum (a[i]-b[i])^2
+typedef float v16f __attribute__((vector_size(64), aligned(4)));
+typedef float v8f __attribute__((vector_size(32), aligned(4)));
+typedef float v4f __attribute__((vector_size(16), aligned(4)));
+
+template <typename V>
+__attribute__((always_inline)) inline V loadu(const float *p) {
+    V v;
+    __builtin_memcpy(&v, p, sizeof(V));
+    return v;
+}
+template <typename V>
+__attribute__((always_inline)) inline V fused(V x, V y, V acc) {  // per-lane fma: one rounding, like vfmadd231ps
+    constexpr int n = sizeof(V) / sizeof(float);
+    V out;
+    for (int l = 0; l < n; ++l) out[l] = __builtin_fmaf(x[l], y[l], acc[l]);
+    return out;
+}
+
+// kSquaredDiff = false: sum a[i]*b[i];  true: sum (a[i]-b[i])^2.
+// Vector-extension code: each `+`/`*` below is one IEEE operation per lane (the build disables contraction),
+// whatever instruction set the clone is compiled for.
 template <bool kSquaredDiff>
-inline float lane_ordered_sum(const float *a, const float *b, unsigned len) {
-    float lanes[16] = {0};
+__attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default"))) inline float lane_ordered_sum(
+    const float *a, const float *b, unsigned len) {
+    v16f lanes = {0};
     unsigned i = 0;
     for (; i + 16 <= len; i += 16) {
-        for (int l = 0; l < 16; ++l) {
-            const float x = kSquaredDiff ? a[i + l] - b[i + l] : a[i + l];
-            const float y = kSquaredDiff ? x : b[i + l];
-            const float prod = x * y;
-            lanes[l] = lanes[l] + prod;
+        v16f x = loadu<v16f>(a + i), y = loadu<v16f>(b + i);
+        if (kSquaredDiff) {
+            x = x - y;
+            y = x;
         }
+        const v16f prod = x * y;
+        lanes = lanes + prod;
     }
-    float oct[8];
+    v8f oct;
     for (int l = 0; l < 8; ++l) oct[l] = lanes[l + 8] + lanes[l];
-    auto fused_tail = [&](float *acc, unsigned width, unsigned count) {
-        for (unsigned l = 0; l < width; ++l) {
-            float x = 0.f, y = 0.f;
-            if (l < count) {
-                x = kSquaredDiff ? a[i + l] - b[i + l] : a[i + l];
-                y = kSquaredDiff ? x : b[i + l];
-            }
-            acc[l] = std::fmaf(x, y, acc[l]);
-        }
-    };
     if (len - i >= 8) {
-        fused_tail(oct, 8, 8);
+        v8f x = loadu<v8f>(a + i), y = loadu<v8f>(b + i);
+        if (kSquaredDiff) {
+            x = x - y;
+            y = x;
+        }
+        oct = fused(x, y, oct);
         i += 8;
     }
-    float quad[4];
+    v4f quad;
     for (int l = 0; l < 4; ++l) quad[l] = oct[l + 4] + oct[l];
     if (len - i >= 4) {
-        fused_tail(quad, 4, 4);
+        v4f x = loadu<v4f>(a + i), y = loadu<v4f>(b + i);
+        if (kSquaredDiff) {
+            x = x - y;
+            y = x;
+        }
+        quad = fused(x, y, quad);
         i += 4;
     }
-    if (len - i > 0) fused_tail(quad, 4, len - i);
+    if (len - i > 0) {  // zero-filled partial vector (masked_read, distance.h:23-36)
+        v4f x = {0, 0, 0, 0}, y = {0, 0, 0, 0};
+        for (unsigned l = 0; l < len - i; ++l) {
+            x[l] = a[i + l];
+            y[l] = b[i + l];
+        }
+        if (kSquaredDiff) {
+            x = x - y;
+            y = x;
+        }
+        quad = fused(x, y, quad);
+    }
     const float lo = quad[0] + quad[1];
     const float hi = quad[2] + quad[3];
     return lo + hi;

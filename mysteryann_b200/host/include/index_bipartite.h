@@ -1,0 +1,80 @@
+// Drop-in for the reference's efanna2e::IndexBipartite (include/index_bipartite.h:23-171), restricted to the
+// RoarGraph path (tests/test_search_roargraph.cpp, tests/test_build_roargraph.cpp).  Same public names and
+// argument meaning; search runs on the GPU through the C ABI in include/roargraph_b200.h, graph construction
+// stays on the host CPU like the reference.  The legacy bipartite methods of the reference are out of scope.
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "efanna2e/index.h"
+#include "efanna2e/neighbor.h"
+#include "efanna2e/parameters.h"
+#include "efanna2e/util.h"
+
+struct rg_index;  // include/roargraph_b200.h
+
+namespace efanna2e {
+
+class IndexBipartite : public Index {
+   public:
+    using CompactGraph = std::vector<std::vector<uint32_t>>;
+
+    // index_bipartite.h:27 - n is ignored by the RoarGraph path (sizes come from the loaded files)
+    explicit IndexBipartite(size_t dimension, size_t n, Metric m, Index *initializer);
+    ~IndexBipartite() override;
+
+    // ---- load / save (src/index_bipartite.cpp:2661-2692, 2097-2117, 2606-2619, 2622-2639) ----
+    void LoadSearchNeededData(const char *base_file, const char *sampled_query_file) {
+        LoadVectorData(base_file, sampled_query_file);
+    }
+    void LoadVectorData(const char *base_file, const char *sampled_query_file);
+    void LoadProjectionGraph(const char *filename);
+    void SaveProjectionGraph(const char *filename);
+    void LoadLearnBaseKNN(const char *filename);
+
+    // ---- search (src/index_bipartite.cpp:2311-2420) ----
+    // Kept for API parity: the GPU path needs no visited-list pool; this uploads the index to the device.
+    void InitVisitedListPool(uint32_t num_threads);
+    // One query = a batch of one (parameters must hold "L_pq").  Returns {cmps, hops}.
+    std::pair<uint32_t, uint32_t> SearchRoarGraph(const float *query, size_t k, size_t &qid,
+                                                  const Parameters &parameters, unsigned *indices,
+                                                  std::vector<float> &res_dists);
+    // What the drop-in driver calls in place of the reference's OpenMP loop: all queries in one launch.
+    // queries: nq rows of GetDimension() floats; indices/dists: nq*k; cmps/hops: nq (may be null).
+    void SearchRoarGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
+                              unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops);
+
+    // ---- build (src/index_bipartite.cpp:143-233) ----
+    void BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data,
+                        const Parameters &parameters);
+
+    CompactGraph &GetProjectionGraph() { return projection_graph_; }
+    std::vector<std::vector<uint32_t>> &GetLearnBaseKNN() { return learn_base_knn_; }
+    uint32_t GetProjectionEp() const { return projection_ep_; }
+    void SetProjectionGraph(uint32_t ep, CompactGraph graph);  // adopt an externally built graph
+    void SetBaseData(const float *base, size_t n);             // adopt caller-owned padded rows
+    void SetDevice(int device) { device_ = device; }
+
+    bool need_normalize = false;  // index_bipartite.h:145 (COSINE)
+
+   private:
+    void upload_to_device();
+    void release_device();
+    // graph construction steps (see src/index_bipartite.cpp file:line in index_bipartite.cpp)
+    void calculate_projection_ep();
+    void link_projection(const Parameters &parameters);
+
+    Index *initializer_;
+    CompactGraph projection_graph_, supply_nbrs_, learn_base_knn_;
+    std::vector<std::mutex> locks_;
+    uint32_t projection_ep_ = 0;
+    float *owned_base_ = nullptr;  // allocated by LoadVectorData, never freed by the reference either
+    rg_index *device_index_ = nullptr;
+    int device_ = 0;
+    std::mutex device_mutex_;
+};
+
+}  // namespace efanna2e

@@ -1,0 +1,53 @@
+// Small extern "C" handle over the host C++ class so the Python harness (tests/, bench.py) can drive the
+// drop-in layer exactly as the CLI drivers do: file in -> BuildRoarGraph -> file out, and file in -> batched search.
+#include <cstring>
+#include <sstream>
+#include <string>
+
+#include "index_bipartite.h"
+
+namespace {
+thread_local std::string g_err;
+struct Mute {  // the build prints progress like the reference; keep harness logs clean
+    std::streambuf *old;
+    std::ostringstream sink;
+    explicit Mute(bool on) : old(on ? std::cout.rdbuf(sink.rdbuf()) : nullptr) {}
+    ~Mute() {
+        if (old) std::cout.rdbuf(old);
+    }
+};
+}  // namespace
+
+extern "C" {
+__attribute__((visibility("default"))) const char *rgh_last_error() { return g_err.c_str(); }
+
+// tests/test_build_roargraph.cpp:105-136 on in-memory arrays.  base/train: padded rows (dim % 8 == 0);
+// knn_ids: n_train x knn_k.  Writes the projection index file.  Returns 0 on success.
+__attribute__((visibility("default"))) int rgh_build_index(const float *base, uint64_t n, const float *train,
+                                                            uint64_t n_train, uint32_t dim, int metric,
+                                                            const uint32_t *knn_ids, uint32_t knn_k, uint32_t M_sq,
+                                                            uint32_t M_pjbp, uint32_t L_pjpq, uint32_t num_threads,
+                                                            const char *out_index, int quiet, double *seconds) {
+    try {
+        Mute mute(quiet != 0);
+        efanna2e::IndexBipartite index(dim, n + n_train, static_cast<efanna2e::Metric>(metric), nullptr);
+        auto &knn = index.GetLearnBaseKNN();
+        knn.resize(n_train);
+        for (uint64_t i = 0; i < n_train; ++i) knn[i].assign(knn_ids + i * knn_k, knn_ids + (i + 1) * knn_k);
+        efanna2e::Parameters p;
+        p.Set<uint32_t>("M_sq", M_sq);
+        p.Set<uint32_t>("M_pjbp", M_pjbp);
+        p.Set<uint32_t>("L_pjpq", L_pjpq);
+        p.Set<uint32_t>("num_threads", num_threads);
+        auto s = std::chrono::high_resolution_clock::now();
+        index.BuildRoarGraph(n_train, train, n, base, p);
+        auto e = std::chrono::high_resolution_clock::now();
+        if (seconds) *seconds = std::chrono::duration<double>(e - s).count();
+        index.SaveProjectionGraph(out_index);
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return 1;
+    }
+}
+}
