@@ -334,7 +334,11 @@ void IndexBipartite::link_projection(const Parameters &parameters) {
     // re-pruned with the newcomer appended.  ProjectionAddReverse :1391-1432 (cap M, prune_reverse with fill)
     // and SupplyAddReverse :1352-1389 (cap 2M, internal prune).
     auto add_reverse = [&](CompactGraph &g, uint32_t src, uint32_t cap, bool internal) {
-        const std::vector<uint32_t> out = g[src];  // the reference iterates the live list; at 1 thread it cannot change
+        std::vector<uint32_t> out;  // snapshot under the owner's lock: other threads may be rewriting g[src]
+        {
+            Guard lk(locks_[src]);
+            out = g[src];
+        }
         for (uint32_t des : out) {
             std::vector<uint32_t> merged;
             {
@@ -411,6 +415,7 @@ void IndexBipartite::link_projection(const Parameters &parameters) {
         NeighborPriorityQueue pool;
         pool.reserve(L_pjpq);
         std::vector<Neighbor> expanded;
+        std::vector<uint32_t> nbrs;
 #pragma omp for schedule(dynamic, 2048)
         for (uint32_t node = 0; node < n; ++node) {
             if (++epoch == 0) {
@@ -425,7 +430,11 @@ void IndexBipartite::link_projection(const Parameters &parameters) {
             while (pool.has_unexpanded_node()) {
                 const Neighbor cur = pool.closest_unexpanded();
                 expanded.push_back(cur);  // :1318
-                for (uint32_t nbr : supply_nbrs_[cur.id]) {
+                {   // the live list may be rewritten by another thread's SupplyAddReverse: copy it under its lock
+                    Guard lk(locks_[cur.id]);
+                    nbrs = supply_nbrs_[cur.id];
+                }
+                for (uint32_t nbr : nbrs) {
                     if (stamp[nbr] == epoch || nbr == node) continue;  // :1327
                     stamp[nbr] = epoch;
                     pool.insert(Neighbor(nbr, distance_->compare(data_bp_ + dimension_ * (size_t)nbr, query, (unsigned)dimension_), false));
