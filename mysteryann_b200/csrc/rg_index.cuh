@@ -41,7 +41,7 @@ struct rg_index {
     cudaStream_t stream = nullptr;  // private stream of the host-buffer API
 
     // tuning (0 = auto)
-    int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0;
+    int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0, cfg_stage_bufs = 0;
 
     uint64_t launches = 0;
 };

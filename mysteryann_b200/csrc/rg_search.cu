@@ -40,6 +40,7 @@ struct SearchParams {
     uint32_t dim, adj_stride, ep, k, L;
     uint32_t hash_log2, hash_limit;
     uint32_t stage_rows;       // rows per staging buffer (multiple of 8)
+    uint32_t stage_bufs;       // 1 = single buffer (more resident warps), 2 = double buffered
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t cand_cap;         // capacity of the candidate arrays (>= adj_stride)
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
@@ -60,54 +61,50 @@ __device__ __forceinline__ bool visited_test_and_set(uint32_t *table, uint32_t l
     }
 }
 
-// ---- distance of 8 staged rows per warp, 4 lanes per row, reference operation order -------------
+// ---- distance of 8 rows per warp, 4 lanes per row, reference operation order ---------------------
 // Lane t (0..3) of a group owns AVX lanes 4t..4t+3 of the reference's 16-lane accumulator.
 template <bool kIP>
-__device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ rp, const float4 *__restrict__ qp,
-                                                      uint32_t n16, bool tail8, uint32_t t) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (uint32_t s = 0; s < n16; ++s) {
-        const float4 v = rp[4 * s];
-        const float4 q = qp[4 * s];
-        if (kIP) {
-            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
-        } else {
-            const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
-                        dw = __fsub_rn(v.w, q.w);
-            acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
-        }
+__device__ __forceinline__ void main_step(float4 &acc, const float4 v, const float4 q) {  // vmulps + vaddps
+    if (kIP) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
+    } else {
+        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
+                    dw = __fsub_rn(v.w, q.w);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
     }
-    // fold 16 -> 8: AVX lane l+8 lives two CUDA lanes up (valid in t < 2)
+}
+template <bool kIP>
+__device__ __forceinline__ void fused_step(float4 &m, const float4 v, const float4 q) {  // vfmadd231ps
+    if (kIP) {
+        m.x = __fmaf_rn(v.x, q.x, m.x);
+        m.y = __fmaf_rn(v.y, q.y, m.y);
+        m.z = __fmaf_rn(v.z, q.z, m.z);
+        m.w = __fmaf_rn(v.w, q.w, m.w);
+    } else {
+        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
+                    dw = __fsub_rn(v.w, q.w);
+        m.x = __fmaf_rn(dx, dx, m.x);
+        m.y = __fmaf_rn(dy, dy, m.y);
+        m.z = __fmaf_rn(dz, dz, m.z);
+        m.w = __fmaf_rn(dw, dw, m.w);
+    }
+}
+// folds 16 -> 8 (AVX lane l+8 lives two CUDA lanes up), the fused 8-wide tail, 8 -> 4, (x0+x1)+(x2+x3)
+template <bool kIP>
+__device__ __forceinline__ float finish_distance(const float4 acc, bool tail8, const float4 vt, const float4 qt,
+                                                  uint32_t t) {
     float4 m;
     m.x = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.x, 2), acc.x);
     m.y = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.y, 2), acc.y);
     m.z = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.z, 2), acc.z);
     m.w = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.w, 2), acc.w);
-    if (tail8 && t < 2) {  // 8-wide fused tail (vfmadd231ps ymm)
-        const float4 v = rp[4 * n16];
-        const float4 q = qp[4 * n16];
-        if (kIP) {
-            m.x = __fmaf_rn(v.x, q.x, m.x);
-            m.y = __fmaf_rn(v.y, q.y, m.y);
-            m.z = __fmaf_rn(v.z, q.z, m.z);
-            m.w = __fmaf_rn(v.w, q.w, m.w);
-        } else {
-            const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
-                        dw = __fsub_rn(v.w, q.w);
-            m.x = __fmaf_rn(dx, dx, m.x);
-            m.y = __fmaf_rn(dy, dy, m.y);
-            m.z = __fmaf_rn(dz, dz, m.z);
-            m.w = __fmaf_rn(dw, dw, m.w);
-        }
-    }
-    // fold 8 -> 4 (valid in t == 0), then the two hadd: (x0+x1)+(x2+x3)
+    if (tail8 && t < 2) fused_step<kIP>(m, vt, qt);
     float4 f;
     f.x = __fadd_rn(__shfl_down_sync(0xffffffffu, m.x, 1), m.x);
     f.y = __fadd_rn(__shfl_down_sync(0xffffffffu, m.y, 1), m.y);
@@ -117,7 +114,53 @@ __device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ 
     return kIP ? -r : r;
 }
 
-// kGather: 1 = cp.async (LDGSTS 16 B per lane), 2 = TMA bulk copy (one UBLKCP per row) on an mbarrier
+// row staged in shared memory (gather modes 1, 2)
+template <bool kIP>
+__device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ rp, const float4 *__restrict__ qp,
+                                                      uint32_t n16, bool tail8, uint32_t t) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (uint32_t s = 0; s < n16; ++s) main_step<kIP>(acc, rp[4 * s], qp[4 * s]);
+    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
+    if (tail8 && t < 2) {
+        vt = rp[4 * n16];
+        qt = qp[4 * n16];
+    }
+    return finish_distance<kIP>(acc, tail8, vt, qt, t);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {  // read-once row data: keep it out of L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// row read straight from HBM into registers (gather mode 3): kChunk 128-bit loads per lane are in flight
+// before the first one is consumed
+template <bool kIP, int kChunk>
+__device__ __forceinline__ float lane_exact_distance_global(const float4 *__restrict__ gp,
+                                                             const float4 *__restrict__ qp, uint32_t n16, bool tail8,
+                                                             uint32_t t) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
+    if (tail8 && t < 2) vt = ldg_stream(gp + 4 * n16);
+    for (uint32_t s0 = 0; s0 < n16; s0 += kChunk) {
+        float4 v[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+            if (s0 + j < n16) v[j] = ldg_stream(gp + 4 * (s0 + j));
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+            if (s0 + j < n16) main_step<kIP>(acc, v[j], qp[4 * (s0 + j)]);
+    }
+    if (tail8 && t < 2) qt = qp[4 * n16];
+    return finish_distance<kIP>(acc, tail8, vt, qt, t);
+}
+
+// kGather: 1 = cp.async (LDGSTS 16 B per lane) into shared memory, 2 = TMA bulk copy (one UBLKCP per row) into shared
+// memory on an mbarrier, 3 = straight into registers (LDG.128, no staging buffer -> more resident warps)
 template <bool kIP, int kGather, bool kGlobalHash>
 __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,7 +226,39 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
     };
     // scores s_cid[0..ncand) -> s_ckey[0..ncand)
     auto score = [&](uint32_t ncand) {
+        if (kGather == 3) {
+            const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
+            for (uint32_t r0 = 0; r0 < ncand; r0 += 8) {
+                const uint32_t r = r0 + grp;
+                const bool valid = r < ncand;
+                const uint32_t id = s_cid[valid ? r : ncand - 1];
+                const float4 *gp = reinterpret_cast<const float4 *>(p.base + size_t(id) * dim) + t;
+                const float d = lane_exact_distance_global<kIP, 8>(gp, qp, n16, tail8, t);
+                if (valid && t == 0) s_ckey[r] = make_key(d, id);
+            }
+            __syncwarp();
+            return;
+        }
         const uint32_t nb = (ncand + BR - 1) / BR;
+        if (p.stage_bufs == 1) {  // overlap comes from the other resident warps
+            for (uint32_t b = 0; b < nb; ++b) {
+                const uint32_t c0 = b * BR;
+                const uint32_t rows = min(BR, ncand - c0);
+                issue(c0, rows, 0);
+                wait_buf(0, false);
+                for (uint32_t r0 = 0; r0 < rows; r0 += 8) {
+                    const uint32_t r = r0 + grp;
+                    const bool valid = r < rows;
+                    const uint32_t rr = valid ? r : rows - 1;
+                    const float4 *rp = reinterpret_cast<const float4 *>(s_stage + size_t(rr) * RS) + t;
+                    const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
+                    const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
+                    if (valid && t == 0) s_ckey[c0 + r] = make_key(d, s_cid[c0 + r]);
+                }
+                __syncwarp();
+            }
+            return;
+        }
         issue(0, min(BR, ncand), 0);
         for (uint32_t b = 0; b < nb; ++b) {
             const uint32_t c0 = b * BR;
@@ -206,12 +281,10 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
     };
 
     uint32_t size = 0, cur = 0;
+    uint64_t tail = ~0ull;  // (distance,id) of the last entry once the pool is full, else +inf (warp-uniform)
     // NeighborPriorityQueue::insert (neighbor.h:150-183) for one key, executed by the whole warp
     auto pool_insert = [&](uint64_t key) {
-        if (size == L) {
-            const uint64_t tail = s_pool[L - 1] & ~1ull;
-            if (key >= tail) return;  // worse than the last entry, or the very same (distance,id)
-        }
+        if (key >= tail) return;  // full pool and worse than its last entry, or the very same (distance,id)
         uint32_t pos = 0;
         bool dup = false;
         for (uint32_t i0 = 0; i0 < size; i0 += 32) {
@@ -234,6 +307,21 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
         __syncwarp();
         if (size < L) ++size;
         if (pos < cur) cur = pos;
+        if (size == L) tail = s_pool[L - 1] & ~1ull;
+    };
+    // all scored candidates of a hop: lanes test their keys against the tail in parallel, survivors are inserted
+    // one by one (the tail only tightens, so a key rejected here would be rejected by insert() as well)
+    auto merge = [&](uint32_t ncand) {
+        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+            const uint64_t key = (c0 + lane < ncand) ? s_ckey[c0 + lane] : ~0ull;
+            uint32_t m = __ballot_sync(0xffffffffu, key < tail);
+            while (m) {
+                const uint32_t b = __ffs(m) - 1;
+                pool_insert(__shfl_sync(0xffffffffu, key, b));
+                m &= m - 1;
+                m &= __ballot_sync(0xffffffffu, key < tail);
+            }
+        }
     };
 
     for (;;) {
@@ -257,6 +345,7 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
 
         size = 0;
         cur = 0;
+        tail = ~0ull;
         uint32_t cmps = 0, hops = 0, nvis = 0;
         bool overflow = false;
 
@@ -324,11 +413,9 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
             nvis += ncand;
             if (ncand == 0) continue;
             score(ncand);
-            for (uint32_t c = 0; c < ncand; ++c) {
-                // a re-scored entry point lands here too; insert() drops it as a duplicate (neighbor.h:161)
-                // or as worse than the tail (neighbor.h:151), exactly like the reference
-                pool_insert(s_ckey[c]);
-            }
+            // a re-scored entry point lands here too; insert() drops it as a duplicate (neighbor.h:161) or as
+            // worse than the tail (neighbor.h:151), exactly like the reference
+            merge(ncand);
         }
 
         if (overflow) {
@@ -398,7 +485,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     // different halves of the 32 banks
     uint32_t rs = (ix->dim % 32 <= 16) ? ix->dim - ix->dim % 32 + 16 : ix->dim - ix->dim % 32 + 48;
     p.row_stride = rs;
-    uint32_t br = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : ((16384u / (rs * 4u)) >= 16 ? 16u : 8u);
+    uint32_t br = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;  // 8 rows x 2 buffers measured best (profiles/)
     p.stage_rows = br;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
 
@@ -419,7 +506,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.off_hash = off;
     if (!g->global_hash) off += (4u << hl);
     p.off_stage = off;
-    off += round_up(2 * br * rs * 4, 128);
+    p.stage_bufs = ix->cfg_stage_bufs ? uint32_t(ix->cfg_stage_bufs) : 2u;
+    if (g->gather != 3) off += round_up(p.stage_bufs * br * rs * 4, 128);
     p.off_mbar = off;
     off += 128;
     p.smem_per_warp = off;
@@ -468,6 +556,10 @@ static cudaError_t launch_one(const Geometry &g, int grid, cudaStream_t st) {
 }
 
 static cudaError_t launch(const Geometry &g, bool ip, int grid, cudaStream_t st) {
+    if (g.gather == 3) {
+        if (g.global_hash) return ip ? launch_one<true, 3, true>(g, grid, st) : launch_one<false, 3, true>(g, grid, st);
+        return ip ? launch_one<true, 3, false>(g, grid, st) : launch_one<false, 3, false>(g, grid, st);
+    }
     if (g.global_hash) {
         if (g.gather == 2) return ip ? launch_one<true, 2, true>(g, grid, st) : launch_one<false, 2, true>(g, grid, st);
         return ip ? launch_one<true, 1, true>(g, grid, st) : launch_one<false, 1, true>(g, grid, st);

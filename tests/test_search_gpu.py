@@ -39,7 +39,7 @@ def capi():
     return capi
 
 
-@pytest.mark.parametrize("gather", (1, 2))
+@pytest.mark.parametrize("gather", (1, 2, 3))
 @pytest.mark.parametrize("name", CASES)
 def test_golden(capi, name, gather):
     c = load_case(name)
@@ -76,7 +76,7 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     if off[ep + 1] == off[ep]:
         ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    for gather in (1, 2):
+    for gather in (1, 2, 3):
         ix.configure(gather=gather)
         for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
             want = oracle.search(base, off, adj, ep, q, k, L, metric=metric)

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--deg", type=int, default=48)
     ap.add_argument("--Ls", type=int, nargs="+", default=[20, 100])
-    ap.add_argument("--configs", type=str, default="1:0:0:0,2:0:0:0,1:0:0:8,2:0:0:8,2:4:0:0,2:2:0:0,1:2:0:0")
+    ap.add_argument("--configs", type=str, default="2:0:0:8,2:0:0:9,2:0:0:17,1:0:0:9")
     ap.add_argument("--out", type=str, default="")
     a = ap.parse_args()
     build.build()
