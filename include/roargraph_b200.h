@@ -106,6 +106,10 @@ RG_API rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_
                                      uint64_t nq, uint32_t K, int metric, uint32_t *d_ids, float *d_dists,
                                      int device, void *cuda_stream);
 
+/* Diagnostics of the last rg_knn_exact* call in this process: kernel launches issued, and how many queries
+ * failed the completeness certificate and were redone by the exact FP32 scan. */
+RG_API void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans);
+
 #ifdef __cplusplus
 }
 #endif

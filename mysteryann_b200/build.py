@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++", "-lcuda"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -21,7 +21,8 @@ METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure",
-           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device"]
+           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device",
+           "rg_knn_last_stats"]
 
 _lib = None
 
@@ -64,6 +65,8 @@ def lib():
     L.rg_knn_exact_device.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, i32, vp]
     L.rg_knn_merge_device.restype = i32
     L.rg_knn_merge_device.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32, vp]
+    L.rg_knn_last_stats.restype = None
+    L.rg_knn_last_stats.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -143,3 +146,37 @@ class Index:
         p = lambda t: None if t is None else t.data_ptr()
         _check(lib().rg_search_batch_device(self._h, p(d_queries), nq, k, L, p(d_ids), p(d_dists), p(d_cmps),
                                             p(d_hops), p(d_status), stream))
+
+
+def knn_exact(base, queries, K, metric=METRIC_IP, id_base=0, device=0):
+    """Exact kNN of numpy host arrays (H2D + kernels + D2H inside).  Returns (ids u32 [nq,K], dists f32 [nq,K])."""
+    base = np.ascontiguousarray(base, np.float32)
+    queries = np.ascontiguousarray(queries, np.float32)
+    n, dim = base.shape
+    nq = queries.shape[0]
+    ids = np.empty((nq, K), np.uint32)
+    dists = np.empty((nq, K), np.float32)
+    _check(lib().rg_knn_exact(_hp(base), n, id_base, _hp(queries), nq, dim, metric, K, _hp(ids), _hp(dists), device))
+    return ids, dists
+
+
+def knn_exact_device(d_base, d_queries, K, d_ids, d_dists, metric=METRIC_IP, id_base=0, stream=None):
+    """Exact kNN on CUDA torch tensors (float32 [n,dim], [nq,dim]; int32 [nq,K], float32 [nq,K])."""
+    n, dim = d_base.shape
+    device = d_base.device.index or 0
+    _check(lib().rg_knn_exact_device(d_base.data_ptr(), n, id_base, d_queries.data_ptr(), d_queries.shape[0], dim,
+                                     metric, K, d_ids.data_ptr(), d_dists.data_ptr(), device, stream))
+
+
+def knn_merge_device(d_part_ids, d_part_dists, d_ids, d_dists, metric=METRIC_IP, stream=None):
+    """K4: merge [G, nq, K] per-shard lists into the global top-K."""
+    G, nq, K = d_part_ids.shape
+    device = d_part_ids.device.index or 0
+    _check(lib().rg_knn_merge_device(d_part_ids.data_ptr(), d_part_dists.data_ptr(), G, nq, K, metric,
+                                     d_ids.data_ptr(), d_dists.data_ptr(), device, stream))
+
+
+def knn_last_stats():
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    lib().rg_knn_last_stats(C.byref(a), C.byref(b))
+    return dict(launches=a.value, exact_scans=b.value)

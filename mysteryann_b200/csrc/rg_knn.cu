@@ -1,17 +1,868 @@
-// K2/K3/K4 - build-time exact kNN (placeholder until the tcgen05 path lands; fails loudly).
+// K2/K3/K4 - build-time exact kNN (replaces exact_knn + the part merge of the DiskANN tool the reference uses,
+// /root/reference thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:126-248, 396-448).
+//
+// The reference materialises a 1024 x npoints FP32 score block in host RAM with MKL sgemm and scans it with a heap
+// per query.  Here the scores never leave the SM:
+//   K2  tcgen05 GEMM (kind::f16, FP16 operands, FP32 accumulate in TMEM) over tiles of 128 queries x 128 base rows;
+//       operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle) in a ring of 64-wide K slabs; the epilogue reads
+//       the accumulators with tcgen05.ld and keeps only the scores that beat the query's current threshold
+//       (appended to a small per-query candidate list) - a threshold-filtered top-k' instead of a heap scan.
+//       The base is visited in blocks of doubling size; after each block K2s (one warp per query) sorts the list,
+//       keeps the best k' and tightens the threshold.
+//   K3  FP32 re-rank of the k' survivors in the reference's lane-ordered arithmetic + a per-query CERTIFICATE:
+//       every point that is not a survivor has approx score >= tau (the worst survivor); the FP16 rounding error of a
+//       score is bounded by eps = 2^-10 |q| max|b| (x2 for L2), so if exact_K < tau - eps the top-K is provably
+//       complete.  Queries that fail the certificate (or whose list overflowed) are redone by an exact FP32 scan.
+//   K4  k-way merge of per-shard lists (multi-GPU: base sharded, lists exchanged with NCCL by the caller).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "rg_common.cuh"
 
+namespace rg {
+namespace knn {
+
+constexpr int kTileM = 128;      // queries per CTA tile (TMEM lanes)
+constexpr int kTileN = 128;      // base rows per MMA tile (TMEM columns per accumulator)
+constexpr int kSlabK = 64;       // FP16 elements per K slab = 128 bytes = one 128B-swizzle row
+constexpr int kSlabBytes = kTileN * kSlabK * 2;  // 16 KB
+constexpr int kUmmaK = 16;
+constexpr int kMaxSlabs = 8;     // dim <= 512
+constexpr int kThreads = 192;    // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner
+constexpr uint32_t kCap = 1024;  // candidate list capacity per query
+constexpr int kChunkTiles = 32;  // base tiles per work unit (A stays resident for a whole unit)
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMA)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {  // arrives on `bar` when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive FP32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor): start>>4 | SBO(1024 B)>>4 <<32 |
+// version 1 <<46 | layout SWIZZLE_128B(2) <<61.  LBO is ignored for swizzled K-major operands.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=F32 (1<<4), A=B=F16 (0), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24.
+constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(kTileN >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP32 -> FP16 slab layout [nslab][rows_pad][64], scaled by a power of two; also squared norms / max |x|
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float *__restrict__ x, uint64_t count, uint32_t *out_bits) {
+    float m = 0.f;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// one warp per row
+__global__ void to_half_slabs_kernel(const float *__restrict__ x, uint64_t rows, uint32_t dim, uint64_t rows_pad,
+                                     uint32_t nslab, float scale, __half *__restrict__ out, float *__restrict__ norms,
+                                     uint32_t *max_norm_bits) {
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < rows_pad; r += nwarps) {
+        float ss = 0.f;
+        for (uint32_t c = lane; c < nslab * kSlabK; c += 32) {
+            float v = (r < rows && c < dim) ? x[r * dim + c] : 0.f;
+            ss += v * v;
+            out[(uint64_t(c / kSlabK) * rows_pad + r) * kSlabK + (c % kSlabK)] = __float2half_rn(v * scale);
+        }
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0 && r < rows) {
+            if (norms) norms[r] = ss;
+            if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(ss));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: GEMM + threshold filter
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmParams {
+    uint32_t nslab;        // K slabs (dim rounded up to 64) / 64
+    uint32_t nq;           // valid queries in this batch
+    uint32_t m_tiles;      // ceil(nq / 128)
+    uint64_t q_rows_pad;   // padded row count of the query slab array
+    uint64_t b_rows_pad;   // padded row count of the base slab array
+    uint64_t row_lo;       // first base row of this block (multiple of 128)
+    uint32_t n_tiles;      // base tiles in this block
+    uint64_t n_valid;      // number of real base rows (ids >= n_valid are padding)
+    uint64_t id_base;      // global id of base row 0
+    int l2;                // 1: score = |b|^2 - 2<q,b> ; 0: score = -<q,b>
+    float inv_scale;       // 1 / (scale_q * scale_b): accumulator -> true <q,b>
+    const float *bnorm;    // |b|^2 per base row (L2 only)
+    const float *thr;      // per-query threshold tau (candidates must be < tau)
+    uint64_t *cand;        // [nq][kCap] keys: ordered(score)<<32 | local row id
+    uint32_t *cand_count;  // [nq]
+    uint32_t n_stages;     // B slab ring depth
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
+                       const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // [A slabs: nslab x 16 KB][B ring: n_stages x 16 KB][barriers][tmem slot][bnorm 2 x 128 floats]
+    unsigned char *smem_a = smem;
+    unsigned char *smem_b = smem + size_t(p.nslab) * kSlabBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + size_t(p.n_stages) * kSlabBytes);
+    uint64_t *full = bars;                      // [n_stages]
+    uint64_t *empty = bars + 16;                // [n_stages]
+    uint64_t *a_full = bars + 32;
+    uint64_t *a_empty = bars + 33;
+    uint64_t *tmem_full = bars + 34;            // [2]
+    uint64_t *tmem_empty = bars + 36;           // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
+    float *s_bn = reinterpret_cast<float *>(bars + 48);  // [2][128]
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < p.n_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t chunks = (p.n_tiles + kChunkTiles - 1) / kChunkTiles;
+    const uint32_t units = chunks * p.m_tiles;  // chunk-major: concurrently running CTAs share the B chunk in L2
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
+                mbar_wait(a_empty, a_phase ^ 1);  // MMAs of the previous unit no longer read A
+                a_phase ^= 1;
+                mbar_arrive_expect_tx(a_full, p.nslab * kSlabBytes);
+                for (uint32_t j = 0; j < p.nslab; ++j)
+                    tma_load_2d(smem_a + size_t(j) * kSlabBytes, &map_q, 0, int(j * p.q_rows_pad + uint64_t(m) * kTileM), a_full);
+                const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
+                    for (uint32_t j = 0; j < p.nslab; ++j) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], kSlabBytes);
+                        tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_b, 0, int(j * p.b_rows_pad + row0), &full[stage]);
+                        if (++stage == p.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const uint32_t c = u / p.m_tiles;
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1;
+                const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * kTileN;
+                    for (uint32_t j = 0; j < p.nslab; ++j) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem_a + size_t(j) * kSlabBytes);
+                        const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * kSlabBytes);
+#pragma unroll
+                        for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k) {
+                            umma_f16(tmem_d, make_sw128_desc(a_addr + k * kUmmaK * 2), make_sw128_desc(b_addr + k * kUmmaK * 2),
+                                     kIdesc, (j | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);  // slab may be overwritten once these MMAs retire
+                        if (++stage == p.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tmem_full[acc]);
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> threshold filter =====================
+        uint32_t acc = 0, acc_phase = 0;
+        const uint32_t row_in_tile = warp * 32 + lane;  // TMEM lane == query row of the tile
+        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
+            const uint32_t q = m * kTileM + row_in_tile;
+            const bool q_valid = q < p.nq;
+            const float tau = q_valid ? p.thr[q] : -INFINITY;
+            uint64_t *my_cand = p.cand + uint64_t(q_valid ? q : 0) * kCap;
+            const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+            for (uint32_t t = t0; t < t1; ++t) {
+                const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
+                if (p.l2) {
+                    const uint64_t r = row0 + row_in_tile;
+                    s_bn[acc * kTileN + row_in_tile] = (r < p.n_valid) ? p.bnorm[r] : INFINITY;
+                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                }
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((warp * 32u) << 16) + acc * kTileN;
+#pragma unroll 1
+                for (uint32_t c0 = 0; c0 < kTileN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    bool any = false;
+                    if (p.l2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float s = fmaf(-2.f * p.inv_scale, __uint_as_float(v[i]), s_bn[acc * kTileN + c0 + i]);
+                            any |= (s < tau);
+                        }
+                    } else {
+                        const float theta = -tau;  // -<q,b> < tau  <=>  <q,b> > -tau
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) any |= (__uint_as_float(v[i]) * p.inv_scale > theta);
+                    }
+                    if (any) {
+#pragma unroll 1
+                        for (int i = 0; i < 32; ++i) {
+                            float s;
+                            if (p.l2) s = fmaf(-2.f * p.inv_scale, __uint_as_float(v[i]), s_bn[acc * kTileN + c0 + i]);
+                            else s = -(__uint_as_float(v[i]) * p.inv_scale);
+                            const uint64_t row = row0 + c0 + i;
+                            if (s < tau && row < p.n_valid) {
+                                const uint32_t pos = atomicAdd(&p.cand_count[q], 1u);
+                                if (pos < kCap) my_cand[pos] = (uint64_t(float_to_ordered(s)) << 32) | uint32_t(row);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-level bitonic sort of n <= P (power of two) keys in shared memory, ascending
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t *s, uint32_t P, uint32_t lane) {
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P; i += 32) {
+                const uint32_t x = i ^ j;
+                if (x > i) {
+                    const uint64_t a = s[i], b = s[x];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b) == asc) {
+                        s[i] = b;
+                        s[x] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// K2s: one warp per query: keep the best kprime candidates (ascending), tighten tau, flag overflow
+__global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_t *cand_count, float *thr,
+                                                          uint32_t *overflow, uint32_t nq, uint32_t kprime) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *s = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * kCap;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    uint32_t n = cand_count[q];
+    if (n > kCap) {  // more survivors than the list holds: the exact scan will redo this query
+        if (lane == 0) overflow[q] = 1;
+        n = kCap;
+    }
+    if (n <= kprime && n != kCap) return;  // nothing to drop (tau stays)
+    uint64_t *list = cand + uint64_t(q) * kCap;
+    const uint32_t P = next_pow2(n);
+    for (uint32_t i = lane; i < P; i += 32) s[i] = (i < n) ? list[i] : ~0ull;
+    __syncwarp();
+    warp_bitonic_sort(s, P, lane);
+    const uint32_t keep = min(n, kprime);
+    for (uint32_t i = lane; i < keep; i += 32) list[i] = s[i];
+    if (lane == 0) {
+        cand_count[q] = keep;
+        if (keep == kprime) thr[q] = ordered_to_float(uint32_t(s[kprime - 1] >> 32));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3: exact FP32 re-rank (reference lane order, same arithmetic as the search kernel) + certificate
+// ---------------------------------------------------------------------------------------------------------------
+// 4 lanes per row, 8 rows per warp step; returns the lane-ordered sum (IP: dot, L2: squared distance) in lane 4g
+template <bool kIP>
+__device__ __forceinline__ float exact_score(const float *__restrict__ a, const float *__restrict__ b, uint32_t dim,
+                                             uint32_t t) {
+    const float4 *ap = reinterpret_cast<const float4 *>(a) + t;
+    const float4 *bp = reinterpret_cast<const float4 *>(b) + t;
+    const uint32_t n16 = dim >> 4;
+    const bool tail8 = (dim & 15u) != 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t s = 0; s < n16; ++s) {
+        const float4 v = ap[4 * s], q = bp[4 * s];
+        if (kIP) {
+            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
+        } else {
+            const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z), dw = __fsub_rn(v.w, q.w);
+            acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
+        }
+    }
+    float4 m;
+    m.x = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.x, 2), acc.x);
+    m.y = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.y, 2), acc.y);
+    m.z = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.z, 2), acc.z);
+    m.w = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.w, 2), acc.w);
+    if (tail8 && t < 2) {
+        const float4 v = ap[4 * n16], q = bp[4 * n16];
+        if (kIP) {
+            m.x = __fmaf_rn(v.x, q.x, m.x);
+            m.y = __fmaf_rn(v.y, q.y, m.y);
+            m.z = __fmaf_rn(v.z, q.z, m.z);
+            m.w = __fmaf_rn(v.w, q.w, m.w);
+        } else {
+            const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z), dw = __fsub_rn(v.w, q.w);
+            m.x = __fmaf_rn(dx, dx, m.x);
+            m.y = __fmaf_rn(dy, dy, m.y);
+            m.z = __fmaf_rn(dz, dz, m.z);
+            m.w = __fmaf_rn(dw, dw, m.w);
+        }
+    }
+    float4 f;
+    f.x = __fadd_rn(__shfl_down_sync(0xffffffffu, m.x, 1), m.x);
+    f.y = __fadd_rn(__shfl_down_sync(0xffffffffu, m.y, 1), m.y);
+    f.z = __fadd_rn(__shfl_down_sync(0xffffffffu, m.z, 1), m.z);
+    f.w = __fadd_rn(__shfl_down_sync(0xffffffffu, m.w, 1), m.w);
+    return __fadd_rn(__fadd_rn(f.x, f.y), __fadd_rn(f.z, f.w));
+}
+
+// one warp per query.  out_ids/out_dists: [nq][K]; need_exact[q] = 1 when the certificate fails.
+template <bool kIP>
+__global__ void __launch_bounds__(128) knn_rerank_kernel(const float *__restrict__ base, const float *__restrict__ queries,
+                                                          uint32_t dim, uint64_t id_base, const uint64_t *__restrict__ cand,
+                                                          const uint32_t *__restrict__ cand_count, const float *__restrict__ thr,
+                                                          const uint32_t *__restrict__ overflow, float eps_factor,
+                                                          float max_bnorm2, uint32_t nq, uint32_t K, uint32_t kprime, uint64_t n_base,
+                                                          uint32_t *__restrict__ out_ids, float *__restrict__ out_dists,
+                                                          uint32_t *__restrict__ need_exact) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 2, t = lane & 3;
+    uint64_t *s = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * kCap;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    const uint32_t n = min(cand_count[q], kCap);
+    const float *qv = queries + uint64_t(q) * dim;
+    const uint64_t *list = cand + uint64_t(q) * kCap;
+    const uint32_t P = max(32u, next_pow2(n));
+    for (uint32_t i = lane; i < P; i += 32) s[i] = ~0ull;
+    __syncwarp();
+    for (uint32_t r0 = 0; r0 < n; r0 += 8) {
+        const uint32_t r = r0 + grp;
+        const bool valid = r < n;
+        const uint32_t row = uint32_t(list[valid ? r : n - 1]);
+        const float e = exact_score<kIP>(base + uint64_t(row) * dim, qv, dim, t);
+        if (valid && t == 0) s[r] = make_key(kIP ? -e : e, row) >> 1;  // ordered(score)<<31 | row  (no flag bit needed)
+    }
+    __syncwarp();
+    warp_bitonic_sort(s, P, lane);
+    // |q| for the error bound
+    const float qq = __shfl_sync(0xffffffffu, exact_score<true>(qv, qv, dim, t), 0);
+    const float qn = sqrtf(qq);
+    bool complete = (n_base <= n);  // every base row was a survivor
+    if (!complete && n >= K) {
+        // tau bounds the APPROXIMATE score of every non-survivor from below.  IP: score = -<q,b>.  L2: the filter's
+        // score is |b|^2 - 2<q,b>, i.e. the true squared distance minus |q|^2.
+        const float tau = thr[q] + (kIP ? 0.f : qq);
+        const float eps = eps_factor * qn + 1e-5f * (qq + max_bnorm2);  // FP16 rounding bound + FP32 evaluation slack
+        const float eK = ordered_to_float(uint32_t(s[K - 1] >> 31));
+        complete = (n >= kprime) && (eK < tau - eps) && overflow[q] == 0;
+    }
+    for (uint32_t i = lane; i < K; i += 32) {
+        if (i < n) {
+            const uint64_t k = s[i];
+            const float sc = ordered_to_float(uint32_t(k >> 31));
+            out_ids[uint64_t(q) * K + i] = uint32_t(id_base + (k & 0x7fffffffull));
+            out_dists[uint64_t(q) * K + i] = kIP ? -sc : sc;  // mips distances are written as +ip (compute_groundtruth.cpp:438-441)
+        } else {
+            out_ids[uint64_t(q) * K + i] = 0xFFFFFFFFu;
+            out_dists[uint64_t(q) * K + i] = 0.f;
+        }
+    }
+    if (lane == 0) need_exact[q] = complete ? 0u : 1u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact scan for the (rare) queries without a certificate: one CTA per flagged query, FP32 lane-ordered scores,
+// per-warp bounded sorted lists merged at the end.  K <= 128.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kIP>
+__global__ void __launch_bounds__(256) knn_exact_scan_kernel(const float *__restrict__ base, uint64_t n, uint64_t id_base,
+                                                              const float *__restrict__ queries, uint32_t dim,
+                                                              const uint32_t *__restrict__ flagged, uint32_t n_flagged,
+                                                              uint32_t K, uint32_t *__restrict__ out_ids,
+                                                              float *__restrict__ out_dists) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    // per warp: 256 keys (K best + 128 staging slots, sorted together when the staging area fills)
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 2, t = lane & 3;
+    const uint32_t nwarps = blockDim.x >> 5;
+    uint64_t *s = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * 256;
+    for (uint32_t f = blockIdx.x; f < n_flagged; f += gridDim.x) {
+        const uint32_t q = flagged[f];
+        const float *qv = queries + uint64_t(q) * dim;
+        for (uint32_t i = lane; i < 256; i += 32) s[i] = ~0ull;
+        __syncwarp();
+        uint32_t fill = 0;            // staging entries in s[128 .. 128+fill)
+        uint64_t worst = ~0ull;       // K-th best so far of this warp
+        for (uint64_t r0 = uint64_t(warp) * 8; r0 < n; r0 += uint64_t(nwarps) * 8) {
+            const uint64_t r = r0 + grp;
+            const bool valid = r < n;
+            const float e = exact_score<kIP>(base + (valid ? r : n - 1) * dim, qv, dim, t);
+            const uint64_t key = make_key(kIP ? -e : e, uint32_t(r)) >> 1;
+            const bool want = valid && t == 0 && key < worst;
+            const uint32_t mask = __ballot_sync(0xffffffffu, want);
+            if (want) s[128 + fill + __popc(mask & lanemask_lt())] = key;
+            fill += __popc(mask);
+            __syncwarp();
+            if (fill > 120) {
+                warp_bitonic_sort(s, 256, lane);
+                for (uint32_t i = 128 + lane; i < 256; i += 32) s[i] = ~0ull;
+                __syncwarp();
+                worst = s[K - 1];
+                fill = 0;
+            }
+        }
+        warp_bitonic_sort(s, 256, lane);
+        __syncthreads();
+        // merge the per-warp lists: warp 0 gathers the K best of each warp and sorts (nwarps*K <= 1024)
+        if (warp == 0) {
+            uint64_t *all = reinterpret_cast<uint64_t *>(sm) + size_t(nwarps) * 256;
+            const uint32_t tot = nwarps * 128;
+            for (uint32_t i = lane; i < 1024; i += 32) {
+                const uint32_t w = i / 128, j = i % 128;
+                all[i] = (i < tot && j < K) ? (reinterpret_cast<uint64_t *>(sm))[size_t(w) * 256 + j] : ~0ull;
+            }
+            __syncwarp();
+            warp_bitonic_sort(all, 1024, lane);
+            for (uint32_t i = lane; i < K; i += 32) {
+                const uint64_t k = all[i];
+                if (k != ~0ull) {
+                    const float sc = ordered_to_float(uint32_t(k >> 31));
+                    out_ids[uint64_t(q) * K + i] = uint32_t(id_base + (k & 0x7fffffffull));
+                    out_dists[uint64_t(q) * K + i] = kIP ? -sc : sc;
+                } else {
+                    out_ids[uint64_t(q) * K + i] = 0xFFFFFFFFu;
+                    out_dists[uint64_t(q) * K + i] = 0.f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void compact_flags_kernel(const uint32_t *__restrict__ flags, uint32_t n, uint32_t *__restrict__ list,
+                                     uint32_t *__restrict__ count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) list[atomicAdd(count, 1u)] = i;
+}
+
+__global__ void fill_f32_kernel(float *p, uint64_t n, float v) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: merge G sorted lists per query (output convention: ids + dists, IP dists as +ip) into the global top-K
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) knn_merge_kernel(const uint32_t *__restrict__ part_ids, const float *__restrict__ part_dists,
+                                                         uint32_t G, uint64_t nq, uint32_t K, int ip,
+                                                         uint32_t *__restrict__ out_ids, float *__restrict__ out_dists) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *s = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * 1024;
+    const uint64_t q = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    const uint32_t tot = G * K;
+    const uint32_t P = max(32u, next_pow2(tot));
+    for (uint32_t i = lane; i < P; i += 32) {
+        uint64_t key = ~0ull;
+        if (i < tot) {
+            const uint32_t g = i / K, j = i % K;
+            const uint32_t id = part_ids[(uint64_t(g) * nq + q) * K + j];
+            const float d = part_dists[(uint64_t(g) * nq + q) * K + j];
+            if (id != 0xFFFFFFFFu) key = (uint64_t(float_to_ordered(ip ? -d : d)) << 32) | id;
+        }
+        s[i] = key;
+    }
+    __syncwarp();
+    warp_bitonic_sort(s, P, lane);
+    for (uint32_t i = lane; i < K; i += 32) {
+        const uint64_t k = (i < P) ? s[i] : ~0ull;
+        if (k != ~0ull) {
+            const float sc = ordered_to_float(uint32_t(k >> 32));
+            out_ids[q * K + i] = uint32_t(k);
+            out_dists[q * K + i] = ip ? -sc : sc;
+        } else {
+            out_ids[q * K + i] = 0xFFFFFFFFu;
+            out_dists[q * K + i] = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// slab array [nslab][rows_pad][64] halves viewed as a 2-D tensor {64, nslab*rows_pad}; box {64, 128}; 128B swizzle
+static rg_status make_slab_map(CUtensorMap *map, const __half *ptr, uint32_t nslab, uint64_t rows_pad) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(RG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {cuuint64_t(kSlabK), cuuint64_t(nslab) * rows_pad};
+    cuuint64_t strides[1] = {cuuint64_t(kSlabK) * sizeof(__half)};
+    cuuint32_t box[2] = {cuuint32_t(kSlabK), cuuint32_t(kTileN)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    return RG_OK;
+}
+
+static float pow2_scale(float maxabs) {  // power of two that brings max|x| into (128, 256]
+    if (!(maxabs > 0.f) || !std::isfinite(maxabs)) return 1.f;
+    int e;
+    std::frexp(maxabs, &e);  // maxabs = m * 2^e, m in [0.5, 1)
+    return std::ldexp(1.f, 8 - e);
+}
+
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T **p, uint64_t count) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), std::max<uint64_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const float *d_queries, uint64_t nq, uint32_t dim,
+                     int metric, uint32_t K, uint32_t *d_ids, float *d_dists, cudaStream_t st, uint64_t *stats) {
+    if (!d_base || !d_queries || !d_ids || !d_dists) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: null argument");
+    if (dim == 0 || dim % 8 != 0 || dim > kMaxSlabs * kSlabK)
+        return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim must be a multiple of 8 in [8, %d]", kMaxSlabs * kSlabK);
+    if (K == 0 || K > 128) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: K must be in [1, 128]");
+    if (n == 0 || n >= (1ull << 31)) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: shard size must be in [1, 2^31)");
+    if (metric != RG_METRIC_L2 && metric != RG_METRIC_INNER_PRODUCT && metric != RG_METRIC_COSINE)
+        return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: unsupported metric %d", metric);
+    if (nq == 0) return RG_OK;
+    const bool ip = metric != RG_METRIC_L2;
+    const uint32_t nslab = (dim + kSlabK - 1) / kSlabK;
+    const uint64_t b_rows_pad = (n + kTileN - 1) / kTileN * kTileN;
+    const uint32_t kprime = std::min<uint32_t>(256, std::max<uint32_t>(2 * K, K + 64));
+    const uint64_t q_batch = 32768;
+    const uint64_t q_rows_pad = (std::min(nq, q_batch) + kTileM - 1) / kTileM * kTileM;
+    int dev = 0, sms = 0, smem_max = 0;
+    RG_CUDA_OK(cudaGetDevice(&dev));
+    RG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RG_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+    Scratch sc;
+    __half *b16 = nullptr, *q16 = nullptr;
+    float *bnorm = nullptr, *thr = nullptr;
+    uint32_t *scal = nullptr, *cand_count = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
+    uint64_t *cand = nullptr;
+    RG_CUDA_OK(sc.alloc(&b16, uint64_t(nslab) * b_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.alloc(&q16, uint64_t(nslab) * q_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.alloc(&bnorm, n));
+    RG_CUDA_OK(sc.alloc(&thr, q_batch));
+    RG_CUDA_OK(sc.alloc(&scal, 8));
+    RG_CUDA_OK(sc.alloc(&cand_count, q_batch));
+    RG_CUDA_OK(sc.alloc(&overflow, q_batch));
+    RG_CUDA_OK(sc.alloc(&need_exact, q_batch));
+    RG_CUDA_OK(sc.alloc(&flag_list, q_batch));
+    RG_CUDA_OK(sc.alloc(&cand, q_batch * kCap));
+
+    // scal[0] = max|b| bits, scal[1] = max |b|^2 bits, scal[2] = max|q| bits, scal[3] = #flagged
+    RG_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
+    absmax_kernel<<<sms * 8, 256, 0, st>>>(d_base, n * dim, scal + 0);
+    absmax_kernel<<<sms * 8, 256, 0, st>>>(d_queries, nq * dim, scal + 2);
+    uint32_t h_scal[8];
+    RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_OK(cudaStreamSynchronize(st));
+    float max_b, max_q;
+    memcpy(&max_b, &h_scal[0], 4);
+    memcpy(&max_q, &h_scal[2], 4);
+    const float scale_b = pow2_scale(max_b), scale_q = pow2_scale(max_q);
+    to_half_slabs_kernel<<<sms * 8, 256, 0, st>>>(d_base, n, dim, b_rows_pad, nslab, scale_b, b16, bnorm, scal + 1);
+    RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_OK(cudaStreamSynchronize(st));
+    float max_bnorm2;
+    memcpy(&max_bnorm2, &h_scal[1], 4);
+    // FP16 rounding: |fl(x) - x| <= 2^-11 |x| per operand -> |<q,b>~ - <q,b>| <= (2^-10 + 2^-22) |q| |b|; 2% slack
+    // covers FP32 accumulation; L2 scores carry the factor 2 of -2<q,b>.
+    const float eps_factor = 1.02f * std::ldexp(1.f, -10) * std::sqrt(max_bnorm2) * (ip ? 1.f : 2.f);
+
+    CUtensorMap map_q, map_b;
+    rg_status s = make_slab_map(&map_b, b16, nslab, b_rows_pad);
+    if (s != RG_OK) return s;
+    s = make_slab_map(&map_q, q16, nslab, q_rows_pad);
+    if (s != RG_OK) return s;
+
+    // B ring depth from the shared-memory budget
+    const size_t fixed = size_t(nslab) * kSlabBytes + 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
+    uint32_t n_stages = uint32_t((size_t(smem_max) - fixed) / kSlabBytes);
+    n_stages = std::min<uint32_t>(n_stages, 16);
+    if (n_stages < 2) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim %u leaves no room for the operand ring", dim);
+    const size_t gemm_smem = size_t(nslab + n_stages) * kSlabBytes + 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
+    const size_t scan_smem = (8 * 256 + 1024) * 8;
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
+
+    uint64_t launches = 5, flagged_total = 0;
+    for (uint64_t q0 = 0; q0 < nq; q0 += q_batch) {
+        const uint32_t bq = uint32_t(std::min<uint64_t>(q_batch, nq - q0));
+        const float *dq = d_queries + q0 * dim;
+        to_half_slabs_kernel<<<sms * 4, 256, 0, st>>>(dq, bq, dim, q_rows_pad, nslab, scale_q, q16, nullptr, nullptr);
+        fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
+        RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
+        RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
+        launches += 2;
+        GemmParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.nslab = nslab;
+        gp.nq = bq;
+        gp.m_tiles = (bq + kTileM - 1) / kTileM;
+        gp.q_rows_pad = q_rows_pad;
+        gp.b_rows_pad = b_rows_pad;
+        gp.n_valid = n;
+        gp.id_base = id_base;
+        gp.l2 = ip ? 0 : 1;
+        gp.inv_scale = 1.f / (scale_q * scale_b);
+        gp.bnorm = bnorm;
+        gp.thr = thr;
+        gp.cand = cand;
+        gp.cand_count = cand_count;
+        gp.n_stages = n_stages;
+        // blocks of doubling size: [0,1024), [1024,2048), [2048,4096), ...  (tau = +inf in the first one: every score
+        // of the first 1024 rows is kept, so the list can never overflow there)
+        uint64_t lo = 0, len = kCap;
+        while (lo < b_rows_pad) {
+            const uint64_t hi = std::min(b_rows_pad, lo + len);
+            gp.row_lo = lo;
+            gp.n_tiles = uint32_t((hi - lo) / kTileN);
+            const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
+            knn_gemm_filter_kernel<<<std::min<uint32_t>(units, sms), kThreads, gemm_smem, st>>>(map_q, map_b, gp);
+            knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(cand, cand_count, thr, overflow, bq, kprime);
+            launches += 2;
+            lo = hi;
+            len = std::max<uint64_t>(len, lo);  // next block as large as everything seen so far
+        }
+        if (ip)
+            knn_rerank_kernel<true><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
+                                                                       eps_factor, max_bnorm2, bq, K, kprime, n, d_ids + q0 * K,
+                                                                       d_dists + q0 * K, need_exact);
+        else
+            knn_rerank_kernel<false><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
+                                                                        eps_factor, max_bnorm2, bq, K, kprime, n, d_ids + q0 * K,
+                                                                        d_dists + q0 * K, need_exact);
+        RG_CUDA_OK(cudaMemsetAsync(scal + 3, 0, sizeof(uint32_t), st));
+        compact_flags_kernel<<<(bq + 255) / 256, 256, 0, st>>>(need_exact, bq, flag_list, scal + 3);
+        uint32_t n_flagged = 0;
+        RG_CUDA_OK(cudaMemcpyAsync(&n_flagged, scal + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        launches += 2;
+        if (n_flagged) {
+            flagged_total += n_flagged;
+            const uint32_t grid = std::min<uint32_t>(n_flagged, uint32_t(sms) * 2);
+            if (ip)
+                knn_exact_scan_kernel<true><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, dq, dim, flag_list, n_flagged, K,
+                                                                          d_ids + q0 * K, d_dists + q0 * K);
+            else
+                knn_exact_scan_kernel<false><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, dq, dim, flag_list, n_flagged, K,
+                                                                           d_ids + q0 * K, d_dists + q0 * K);
+            launches += 1;
+        }
+        RG_CUDA_OK(cudaGetLastError());
+    }
+    RG_CUDA_OK(cudaStreamSynchronize(st));
+    if (stats) {
+        stats[0] = launches;
+        stats[1] = flagged_total;
+    }
+    return RG_OK;
+}
+
+}  // namespace knn
+}  // namespace rg
+
+static uint64_t g_knn_stats[2] = {0, 0};
+
 extern "C" {
-rg_status rg_knn_exact(const float *, uint64_t, uint64_t, const float *, uint64_t, uint32_t, int, uint32_t,
-                       uint32_t *, float *, int) {
-    return rg::fail(RG_ERR_INTERNAL, "rg_knn_exact: not implemented yet");
+
+rg_status rg_knn_exact_device(const float *d_base, uint64_t n, uint64_t id_base, const float *d_queries, uint64_t nq,
+                              uint32_t dim, int metric, uint32_t K, uint32_t *d_ids, float *d_dists, int device,
+                              void *cuda_stream) {
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    return rg::knn::knn_device(d_base, n, id_base, d_queries, nq, dim, metric, K, d_ids, d_dists,
+                               static_cast<cudaStream_t>(cuda_stream), g_knn_stats);
 }
-rg_status rg_knn_exact_device(const float *, uint64_t, uint64_t, const float *, uint64_t, uint32_t, int, uint32_t,
-                              uint32_t *, float *, int, void *) {
-    return rg::fail(RG_ERR_INTERNAL, "rg_knn_exact_device: not implemented yet");
+
+rg_status rg_knn_exact(const float *base, uint64_t n, uint64_t id_base, const float *queries, uint64_t nq, uint32_t dim,
+                       int metric, uint32_t K, uint32_t *ids, float *dists, int device) {
+    if (!base || !queries || !ids || !dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: null argument");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    rg::knn::Scratch sc;
+    float *d_base = nullptr, *d_q = nullptr, *d_d = nullptr;
+    uint32_t *d_i = nullptr;
+    RG_CUDA_OK(sc.alloc(&d_base, n * dim));
+    RG_CUDA_OK(sc.alloc(&d_q, nq * dim));
+    RG_CUDA_OK(sc.alloc(&d_i, nq * K));
+    RG_CUDA_OK(sc.alloc(&d_d, nq * K));
+    RG_CUDA_OK(cudaMemcpy(d_base, base, n * dim * sizeof(float), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMemcpy(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice));
+    rg_status s = rg::knn::knn_device(d_base, n, id_base, d_q, nq, dim, metric, K, d_i, d_d, nullptr, g_knn_stats);
+    if (s != RG_OK) return s;
+    RG_CUDA_OK(cudaMemcpy(ids, d_i, nq * K * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    RG_CUDA_OK(cudaMemcpy(dists, d_d, nq * K * sizeof(float), cudaMemcpyDeviceToHost));
+    return RG_OK;
 }
-rg_status rg_knn_merge_device(const uint32_t *, const float *, uint32_t, uint64_t, uint32_t, int, uint32_t *,
-                              float *, int, void *) {
-    return rg::fail(RG_ERR_INTERNAL, "rg_knn_merge_device: not implemented yet");
+
+rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_part_dists, uint32_t G, uint64_t nq, uint32_t K,
+                              int metric, uint32_t *d_ids, float *d_dists, int device, void *cuda_stream) {
+    if (!d_part_ids || !d_part_dists || !d_ids || !d_dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_merge_device: null argument");
+    if (G == 0 || K == 0 || uint64_t(G) * K > 1024) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_merge_device: need 1 <= G*K <= 1024");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    if (nq == 0) return RG_OK;
+    rg::DeviceGuard guard(device);
+    RG_CUDA_OK(cudaFuncSetAttribute(rg::knn::knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 1024 * 8));
+    rg::knn::knn_merge_kernel<<<unsigned((nq + 3) / 4), 128, 4 * 1024 * 8, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_part_ids, d_part_dists, G, nq, K, metric != RG_METRIC_L2 ? 1 : 0, d_ids, d_dists);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+// launches / queries that needed the exact scan in the last rg_knn_exact* call of this process
+void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans) {
+    if (launches) *launches = g_knn_stats[0];
+    if (exact_scans) *exact_scans = g_knn_stats[1];
 }
 }
