@@ -28,13 +28,14 @@
 namespace rg {
 namespace knn {
 
-constexpr int kTileM = 128;      // queries per CTA tile (TMEM lanes)
+constexpr int kTileM = 128;      // queries per MMA (TMEM lanes); a CTA keeps 1 or 2 such halves resident
 constexpr int kTileN = 128;      // base rows per MMA tile (TMEM columns per accumulator)
 constexpr int kSlabK = 64;       // FP16 elements per K slab = 128 bytes = one 128B-swizzle row
 constexpr int kSlabBytes = kTileN * kSlabK * 2;  // 16 KB
 constexpr int kUmmaK = 16;
 constexpr int kMaxSlabs = 8;     // dim <= 512
-constexpr int kThreads = 192;    // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner
+constexpr int kEpiWarps = 8;     // epilogue warps: warp w reads TMEM lanes 32*(w%4).., column half w/4
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // + warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
 constexpr uint32_t kCap = 1024;  // candidate list capacity per query
 constexpr int kChunkTiles = 32;  // base tiles per work unit (A stays resident for a whole unit)
 
@@ -65,6 +66,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (low word, shared high word): low = smem address >> 4 (advance 2 per 32-byte K step)
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {  // arrives on `bar` when all prior MMAs of this thread retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                  : "memory");
@@ -92,6 +103,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
+// Generic K-major swizzled descriptor: layout 2 = 128B (64 halves per row), 4 = 64B (32 halves), 6 = 32B (16 halves);
+// SBO = 8 rows x row bytes.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t layout, uint32_t sbo_bytes) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(layout) << 61);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=F32 (1<<4), A=B=F16 (0), K-major both,
 // N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(kTileN >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
@@ -107,19 +123,23 @@ __global__ void absmax_kernel(const float *__restrict__ x, uint64_t count, uint3
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
 }
 
-// one warp per row
+// one warp per row: columns [0, n_full*64) go to the full-slab array [n_full][rows_pad][64], the remaining
+// columns (zero padded to tail_k) to the tail array [rows_pad][tail_k]
 __global__ void to_half_slabs_kernel(const float *__restrict__ x, uint64_t rows, uint32_t dim, uint64_t rows_pad,
-                                     uint32_t nslab, float scale, __half *__restrict__ out, float *__restrict__ norms,
-                                     uint32_t *max_norm_bits) {
+                                     uint32_t n_full, uint32_t tail_k, float scale, __half *__restrict__ out_full,
+                                     __half *__restrict__ out_tail, float *__restrict__ norms, uint32_t *max_norm_bits) {
     const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    const uint32_t kfull = n_full * kSlabK;
     for (uint64_t r = warp; r < rows_pad; r += nwarps) {
         float ss = 0.f;
-        for (uint32_t c = lane; c < nslab * kSlabK; c += 32) {
+        for (uint32_t c = lane; c < kfull + tail_k; c += 32) {
             float v = (r < rows && c < dim) ? x[r * dim + c] : 0.f;
             ss += v * v;
-            out[(uint64_t(c / kSlabK) * rows_pad + r) * kSlabK + (c % kSlabK)] = __float2half_rn(v * scale);
+            const __half h = __float2half_rn(v * scale);
+            if (c < kfull) out_full[(uint64_t(c / kSlabK) * rows_pad + r) * kSlabK + (c % kSlabK)] = h;
+            else out_tail[r * tail_k + (c - kfull)] = h;
         }
         for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0 && r < rows) {
@@ -133,11 +153,14 @@ __global__ void to_half_slabs_kernel(const float *__restrict__ x, uint64_t rows,
 // K2: GEMM + threshold filter
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmParams {
-    uint32_t nslab;        // K slabs (dim rounded up to 64) / 64
+    uint32_t n_full;       // full 64-wide K slabs (128B swizzle)
+    uint32_t tail_k;       // 0, 16 (32B swizzle) or 32 (64B swizzle): width of the last, narrower K slab
+    uint32_t mh;           // query halves of 128 rows resident per CTA (1 or 2): B traffic per FLOP ~ 1/mh
+    uint32_t a_half_bytes; // shared-memory bytes of one A half (all its slabs)
     uint32_t nq;           // valid queries in this batch
-    uint32_t m_tiles;      // ceil(nq / 128)
-    uint64_t q_rows_pad;   // padded row count of the query slab array
-    uint64_t b_rows_pad;   // padded row count of the base slab array
+    uint32_t m_tiles;      // ceil(nq / (128*mh))
+    uint64_t q_rows_pad;   // padded row count of the query arrays
+    uint64_t b_rows_pad;   // padded row count of the base arrays
     uint64_t row_lo;       // first base row of this block (multiple of 128)
     uint32_t n_tiles;      // base tiles in this block
     uint64_t n_valid;      // number of real base rows (ids >= n_valid are padding)
@@ -152,12 +175,13 @@ struct GemmParams {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
+knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
+                       const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bt,
                        const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // [A slabs: nslab x 16 KB][B ring: n_stages x 16 KB][barriers][tmem slot][bnorm 2 x 128 floats]
+    // [A: mh halves x a_half_bytes][B ring: n_stages x 16 KB][barriers][tmem slot][bnorm 2 x 128 floats]
     unsigned char *smem_a = smem;
-    unsigned char *smem_b = smem + size_t(p.nslab) * kSlabBytes;
+    unsigned char *smem_b = smem + size_t(p.mh) * p.a_half_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + size_t(p.n_stages) * kSlabBytes);
     uint64_t *full = bars;                      // [n_stages]
     uint64_t *empty = bars + 16;                // [n_stages]
@@ -169,6 +193,9 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     float *s_bn = reinterpret_cast<float *>(bars + 48);  // [2][128]
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nslab = p.n_full + (p.tail_k ? 1u : 0u);
+    const uint32_t tail_bytes = kTileN * p.tail_k * 2;
+    const uint32_t tmem_cols = p.mh * 2 * kTileN;  // 256 or 512
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
@@ -178,11 +205,11 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         mbar_init(a_empty, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);
+            mbar_init(&tmem_empty[a], kEpiWarps);
         }
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -190,8 +217,9 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
     const uint32_t chunks = (p.n_tiles + kChunkTiles - 1) / kChunkTiles;
     const uint32_t units = chunks * p.m_tiles;  // chunk-major: concurrently running CTAs share the B chunk in L2
+    const uint32_t rows_per_cta = kTileM * p.mh;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_phase = 0;
@@ -199,16 +227,26 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
                 mbar_wait(a_empty, a_phase ^ 1);  // MMAs of the previous unit no longer read A
                 a_phase ^= 1;
-                mbar_arrive_expect_tx(a_full, p.nslab * kSlabBytes);
-                for (uint32_t j = 0; j < p.nslab; ++j)
-                    tma_load_2d(smem_a + size_t(j) * kSlabBytes, &map_q, 0, int(j * p.q_rows_pad + uint64_t(m) * kTileM), a_full);
+                mbar_arrive_expect_tx(a_full, p.mh * (p.n_full * kSlabBytes + tail_bytes));
+                for (uint32_t h = 0; h < p.mh; ++h) {
+                    unsigned char *ah = smem_a + size_t(h) * p.a_half_bytes;
+                    const uint64_t qrow = uint64_t(m) * rows_per_cta + h * kTileM;
+                    for (uint32_t j = 0; j < p.n_full; ++j)
+                        tma_load_2d(ah + size_t(j) * kSlabBytes, &map_q, 0, int(j * p.q_rows_pad + qrow), a_full);
+                    if (p.tail_k) tma_load_2d(ah + size_t(p.n_full) * kSlabBytes, &map_qt, 0, int(qrow), a_full);
+                }
                 const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
                 for (uint32_t t = t0; t < t1; ++t) {
                     const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
-                    for (uint32_t j = 0; j < p.nslab; ++j) {
+                    for (uint32_t j = 0; j < nslab; ++j) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full[stage], kSlabBytes);
-                        tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_b, 0, int(j * p.b_rows_pad + row0), &full[stage]);
+                        if (j < p.n_full) {
+                            mbar_arrive_expect_tx(&full[stage], kSlabBytes);
+                            tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_b, 0, int(j * p.b_rows_pad + row0), &full[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], tail_bytes);
+                            tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_bt, 0, int(row0), &full[stage]);
+                        }
                         if (++stage == p.n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -217,30 +255,59 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+            // descriptor words: low = (smem address >> 4) & 0x3FFF, high = SBO>>4 | version 1 <<14 | layout <<29
+            const uint32_t hi_full = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t hi_tail = ((8u * p.tail_k * 2u) >> 4) | (1u << 14) | ((p.tail_k == 32 ? 4u : 6u) << 29);
+            const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
+            const uint32_t a_half16 = p.a_half_bytes >> 4;
+            const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+            const bool two = p.mh == 2;
             for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const uint32_t c = u / p.m_tiles;
                 mbar_wait(a_full, a_phase);
                 a_phase ^= 1;
                 const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
                 for (uint32_t t = t0; t < t1; ++t) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator set
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * kTileN;
-                    for (uint32_t j = 0; j < p.nslab; ++j) {
+                    const uint32_t tmem_d = tmem_base + acc * (p.mh * kTileN);
+                    for (uint32_t j = 0; j < p.n_full; ++j) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem_a + size_t(j) * kSlabBytes);
-                        const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * kSlabBytes);
+                        const uint32_t b_lo = b_lo0 + stage * (kSlabBytes >> 4);
+                        const uint32_t a_lo = a_lo0 + j * (kSlabBytes >> 4);
 #pragma unroll
-                        for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k) {
-                            umma_f16(tmem_d, make_sw128_desc(a_addr + k * kUmmaK * 2), make_sw128_desc(b_addr + k * kUmmaK * 2),
-                                     kIdesc, (j | k) != 0 ? 1u : 0u);
+                        for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k)
+                            umma_f16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, hi_full, kIdesc, (j | k) != 0 ? 1u : 0u);
+                        if (two) {
+#pragma unroll
+                            for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k)
+                                umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16 + 2 * k, b_lo + 2 * k, hi_full, kIdesc,
+                                              (j | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(&empty[stage]);  // slab may be overwritten once these MMAs retire
+                        if (++stage == p.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    if (p.tail_k) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo0 + stage * (kSlabBytes >> 4);
+                        const uint32_t a_lo = a_lo0 + p.n_full * (kSlabBytes >> 4);
+                        const uint32_t first = p.n_full ? 1u : 0u;
+                        umma_f16_lohi(tmem_d, a_lo, b_lo, hi_tail, kIdesc, first);
+                        if (p.tail_k == 32) umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, hi_tail, kIdesc, 1u);
+                        if (two) {
+                            umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16, b_lo, hi_tail, kIdesc, first);
+                            if (p.tail_k == 32) umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16 + 2, b_lo + 2, hi_tail, kIdesc, 1u);
+                        }
+                        umma_commit(&empty[stage]);
                         if (++stage == p.n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -257,51 +324,72 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> threshold filter =====================
+        // mh == 2: warp w owns query half w/4 (all 128 columns); mh == 1: warps w and w+4 split the columns.
         uint32_t acc = 0, acc_phase = 0;
-        const uint32_t row_in_tile = warp * 32 + lane;  // TMEM lane == query row of the tile
+        const uint32_t quarter = warp & 3, part = warp >> 2;
+        const uint32_t h = (p.mh == 2) ? part : 0u;
+        const uint32_t col_lo = (p.mh == 2) ? 0u : part * (kTileN / 2);
+        const uint32_t col_hi = (p.mh == 2) ? uint32_t(kTileN) : (part + 1) * (kTileN / 2);
+        const uint32_t row_in_cta = h * kTileM + quarter * 32 + lane;  // TMEM lane (+ half) == query row of the CTA tile
         for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
             const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
-            const uint32_t q = m * kTileM + row_in_tile;
+            const uint32_t q = m * rows_per_cta + row_in_cta;
             const bool q_valid = q < p.nq;
             const float tau = q_valid ? p.thr[q] : -INFINITY;
+            const float scale = 1.f / p.inv_scale;            // power of two
+            const float theta_raw = -tau * scale;             // IP threshold on the raw accumulator
+            const float half_scale = 0.5f * scale;            // L2
+            const float theta_l2 = -tau * half_scale;
             uint64_t *my_cand = p.cand + uint64_t(q_valid ? q : 0) * kCap;
             const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
             for (uint32_t t = t0; t < t1; ++t) {
                 const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
                 if (p.l2) {
-                    const uint64_t r = row0 + row_in_tile;
-                    s_bn[acc * kTileN + row_in_tile] = (r < p.n_valid) ? p.bnorm[r] : INFINITY;
-                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                    if (part == 0) {
+                        const uint64_t r = row0 + quarter * 32 + lane;
+                        s_bn[acc * kTileN + quarter * 32 + lane] = (r < p.n_valid) ? p.bnorm[r] : INFINITY;
+                    }
+                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((warp * 32u) << 16) + acc * kTileN;
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (p.mh * kTileN) + h * kTileN;
 #pragma unroll 1
-                for (uint32_t c0 = 0; c0 < kTileN; c0 += 32) {
+                for (uint32_t c0 = col_lo; c0 < col_hi; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
-                    bool any = false;
+                    // "does any of my 32 accumulators beat the threshold": a max tree (no serial predicate chain) and one
+                    // compare on the raw, scaled value; v[] is only indexed with constants so it stays in registers.
+                    //   IP: -<q,b> < tau            <=>  acc > -tau * scale
+                    //   L2: |b|^2 - 2<q,b> < tau    <=>  acc - |b|^2 * scale/2 > -tau * scale/2
+                    float d[32];
                     if (p.l2) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float s = fmaf(-2.f * p.inv_scale, __uint_as_float(v[i]), s_bn[acc * kTileN + c0 + i]);
-                            any |= (s < tau);
-                        }
+                        for (int i = 0; i < 32; ++i) d[i] = fmaf(-half_scale, s_bn[acc * kTileN + c0 + i], __uint_as_float(v[i]));
                     } else {
-                        const float theta = -tau;  // -<q,b> < tau  <=>  <q,b> > -tau
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) any |= (__uint_as_float(v[i]) * p.inv_scale > theta);
+                        for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
                     }
-                    if (any) {
-#pragma unroll 1
+                    float mx[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) mx[i] = fmaxf(d[i], d[i + 16]);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; ++i) mx[i] = fmaxf(mx[i], mx[i + w]);
+                    const float theta = p.l2 ? theta_l2 : theta_raw;
+                    const bool any = mx[0] > theta;
+                    if (any) {  // rare: a few candidates per query per block
+#pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float s;
-                            if (p.l2) s = fmaf(-2.f * p.inv_scale, __uint_as_float(v[i]), s_bn[acc * kTileN + c0 + i]);
-                            else s = -(__uint_as_float(v[i]) * p.inv_scale);
-                            const uint64_t row = row0 + c0 + i;
-                            if (s < tau && row < p.n_valid) {
-                                const uint32_t pos = atomicAdd(&p.cand_count[q], 1u);
-                                if (pos < kCap) my_cand[pos] = (uint64_t(float_to_ordered(s)) << 32) | uint32_t(row);
+                            const float a = __uint_as_float(v[i]);
+                            if (d[i] > theta) {
+                                const uint64_t row = row0 + c0 + i;
+                                const float sc = p.l2 ? fmaf(-2.f * p.inv_scale, a, s_bn[acc * kTileN + c0 + i]) : -(a * p.inv_scale);
+                                if (row < p.n_valid) {
+                                    const uint32_t pos = atomicAdd(&p.cand_count[q], 1u);
+                                    if (pos < kCap) my_cand[pos] = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
+                                }
                             }
                         }
                     }
@@ -318,7 +406,7 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 256);
+    if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -621,16 +709,19 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// slab array [nslab][rows_pad][64] halves viewed as a 2-D tensor {64, nslab*rows_pad}; box {64, 128}; 128B swizzle
-static rg_status make_slab_map(CUtensorMap *map, const __half *ptr, uint32_t nslab, uint64_t rows_pad) {
+// array [outer][width] halves viewed as a 2-D tensor {width, outer}; box {width, 128}; swizzle = row bytes
+// (full slabs: width 64 -> 128B, outer = n_full*rows_pad; tail: width 16/32 -> 32B/64B, outer = rows_pad)
+static rg_status make_slab_map(CUtensorMap *map, const __half *ptr, uint32_t width, uint64_t outer) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(RG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {cuuint64_t(kSlabK), cuuint64_t(nslab) * rows_pad};
-    cuuint64_t strides[1] = {cuuint64_t(kSlabK) * sizeof(__half)};
-    cuuint32_t box[2] = {cuuint32_t(kSlabK), cuuint32_t(kTileN)};
+    cuuint64_t dims[2] = {cuuint64_t(width), cuuint64_t(outer)};
+    cuuint64_t strides[1] = {cuuint64_t(width) * sizeof(__half)};
+    cuuint32_t box[2] = {cuuint32_t(width), cuuint32_t(kTileN)};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = width == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : width == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
     return RG_OK;
@@ -667,23 +758,35 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: unsupported metric %d", metric);
     if (nq == 0) return RG_OK;
     const bool ip = metric != RG_METRIC_L2;
-    const uint32_t nslab = (dim + kSlabK - 1) / kSlabK;
+    // K split: full 64-wide slabs + one narrower tail slab (16 or 32 wide) when that saves tensor work
+    uint32_t n_full = dim / kSlabK, tail_k = 0;
+    {
+        const uint32_t rem = dim % kSlabK;
+        if (rem > 32) n_full += 1;          // 33..63 left: pad to a full slab
+        else if (rem > 16) tail_k = 32;
+        else if (rem > 0) tail_k = 16;
+    }
+    const uint32_t nslab = n_full + (tail_k ? 1 : 0);
+    const uint32_t tail_bytes = kTileN * tail_k * 2;
+    const uint32_t a_half_bytes = (n_full * kSlabBytes + tail_bytes + 1023) / 1024 * 1024;
     const uint64_t b_rows_pad = (n + kTileN - 1) / kTileN * kTileN;
-    const uint32_t kprime = std::min<uint32_t>(256, std::max<uint32_t>(2 * K, K + 64));
+    const uint32_t kprime = std::min<uint32_t>(256, std::max<uint32_t>(K + K / 2, K + 32));
     const uint64_t q_batch = 32768;
-    const uint64_t q_rows_pad = (std::min(nq, q_batch) + kTileM - 1) / kTileM * kTileM;
+    const uint64_t q_rows_pad = (std::min(nq, q_batch) + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
     int dev = 0, sms = 0, smem_max = 0;
     RG_CUDA_OK(cudaGetDevice(&dev));
     RG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     RG_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
     Scratch sc;
-    __half *b16 = nullptr, *q16 = nullptr;
+    __half *b16 = nullptr, *q16 = nullptr, *b16t = nullptr, *q16t = nullptr;
     float *bnorm = nullptr, *thr = nullptr;
     uint32_t *scal = nullptr, *cand_count = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
     uint64_t *cand = nullptr;
-    RG_CUDA_OK(sc.alloc(&b16, uint64_t(nslab) * b_rows_pad * kSlabK));
-    RG_CUDA_OK(sc.alloc(&q16, uint64_t(nslab) * q_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.alloc(&b16, uint64_t(n_full) * b_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.alloc(&q16, uint64_t(n_full) * q_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.alloc(&b16t, b_rows_pad * std::max<uint32_t>(tail_k, 16)));
+    RG_CUDA_OK(sc.alloc(&q16t, q_rows_pad * std::max<uint32_t>(tail_k, 16)));
     RG_CUDA_OK(sc.alloc(&bnorm, n));
     RG_CUDA_OK(sc.alloc(&thr, q_batch));
     RG_CUDA_OK(sc.alloc(&scal, 8));
@@ -704,7 +807,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     memcpy(&max_b, &h_scal[0], 4);
     memcpy(&max_q, &h_scal[2], 4);
     const float scale_b = pow2_scale(max_b), scale_q = pow2_scale(max_q);
-    to_half_slabs_kernel<<<sms * 8, 256, 0, st>>>(d_base, n, dim, b_rows_pad, nslab, scale_b, b16, bnorm, scal + 1);
+    to_half_slabs_kernel<<<sms * 8, 256, 0, st>>>(d_base, n, dim, b_rows_pad, n_full, tail_k, scale_b, b16, b16t, bnorm, scal + 1);
     RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
     RG_CUDA_OK(cudaStreamSynchronize(st));
     float max_bnorm2;
@@ -713,18 +816,31 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     // covers FP32 accumulation; L2 scores carry the factor 2 of -2<q,b>.
     const float eps_factor = 1.02f * std::ldexp(1.f, -10) * std::sqrt(max_bnorm2) * (ip ? 1.f : 2.f);
 
-    CUtensorMap map_q, map_b;
-    rg_status s = make_slab_map(&map_b, b16, nslab, b_rows_pad);
-    if (s != RG_OK) return s;
-    s = make_slab_map(&map_q, q16, nslab, q_rows_pad);
-    if (s != RG_OK) return s;
+    CUtensorMap map_q, map_b, map_qt, map_bt;
+    rg_status s = RG_OK;
+    if (n_full) {
+        if ((s = make_slab_map(&map_b, b16, kSlabK, uint64_t(n_full) * b_rows_pad)) != RG_OK) return s;
+        if ((s = make_slab_map(&map_q, q16, kSlabK, uint64_t(n_full) * q_rows_pad)) != RG_OK) return s;
+    }
+    if ((s = make_slab_map(&map_bt, b16t, tail_k ? tail_k : 16, b_rows_pad)) != RG_OK) return s;
+    if ((s = make_slab_map(&map_qt, q16t, tail_k ? tail_k : 16, q_rows_pad)) != RG_OK) return s;
+    if (!n_full) {  // never dereferenced by the kernel, but must be valid kernel arguments
+        map_b = map_bt;
+        map_q = map_qt;
+    }
 
     // B ring depth from the shared-memory budget
-    const size_t fixed = size_t(nslab) * kSlabBytes + 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
-    uint32_t n_stages = uint32_t((size_t(smem_max) - fixed) / kSlabBytes);
+    // two resident query halves (M = 256 per B slab: half the L2->SM operand traffic per FLOP) when the ring still
+    // gets >= 4 stages, else one
+    const size_t misc = 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
+    uint32_t mh = 2;
+    if (size_t(smem_max) < 2 * size_t(a_half_bytes) + 4 * size_t(kSlabBytes) + misc) mh = 1;
+    if (size_t(smem_max) < size_t(mh) * a_half_bytes + 2 * size_t(kSlabBytes) + misc)
+        return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim %u leaves no room for the operand ring", dim);
+    uint32_t n_stages = uint32_t((size_t(smem_max) - misc - size_t(mh) * a_half_bytes) / kSlabBytes);
     n_stages = std::min<uint32_t>(n_stages, 16);
-    if (n_stages < 2) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim %u leaves no room for the operand ring", dim);
-    const size_t gemm_smem = size_t(nslab + n_stages) * kSlabBytes + 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
+    const size_t gemm_smem = size_t(mh) * a_half_bytes + size_t(n_stages) * kSlabBytes + misc;
+    (void)nslab;
     RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
@@ -737,16 +853,19 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     for (uint64_t q0 = 0; q0 < nq; q0 += q_batch) {
         const uint32_t bq = uint32_t(std::min<uint64_t>(q_batch, nq - q0));
         const float *dq = d_queries + q0 * dim;
-        to_half_slabs_kernel<<<sms * 4, 256, 0, st>>>(dq, bq, dim, q_rows_pad, nslab, scale_q, q16, nullptr, nullptr);
+        to_half_slabs_kernel<<<sms * 4, 256, 0, st>>>(dq, bq, dim, q_rows_pad, n_full, tail_k, scale_q, q16, q16t, nullptr, nullptr);
         fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
         RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
         RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
         launches += 2;
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
-        gp.nslab = nslab;
+        gp.n_full = n_full;
+        gp.tail_k = tail_k;
+        gp.mh = mh;
+        gp.a_half_bytes = a_half_bytes;
         gp.nq = bq;
-        gp.m_tiles = (bq + kTileM - 1) / kTileM;
+        gp.m_tiles = (bq + kTileM * mh - 1) / (kTileM * mh);
         gp.q_rows_pad = q_rows_pad;
         gp.b_rows_pad = b_rows_pad;
         gp.n_valid = n;
@@ -766,7 +885,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             gp.row_lo = lo;
             gp.n_tiles = uint32_t((hi - lo) / kTileN);
             const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
-            knn_gemm_filter_kernel<<<std::min<uint32_t>(units, sms), kThreads, gemm_smem, st>>>(map_q, map_b, gp);
+            knn_gemm_filter_kernel<<<std::min<uint32_t>(units, sms), kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
             knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(cand, cand_count, thr, overflow, bq, kprime);
             launches += 2;
             lo = hi;
