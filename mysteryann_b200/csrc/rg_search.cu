@@ -16,6 +16,7 @@
 // Within a hop the order of insertion does not change the final pool (bounded sorted set under the
 // strict order (distance,id)), so steps 3-6 are batch operations with bit-identical results.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "rg_index.cuh"
@@ -461,6 +462,12 @@ struct Geometry {
 
 static uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// experiment knobs (tuning sweeps only; 0 / unset = automatic)
+static int env_int(const char *name, int def) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : def;
+}
+
 static uint32_t auto_hash_log2(uint32_t L) {
     // expected worst-case visited nodes per query ~ 1000 + 30 L (max cmps 1371 @L=10 ...
     // 13702 @L=500); outliers take the exact global-table fallback, so this only affects speed.
@@ -491,7 +498,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L);
     p.fallback = fallback ? 1u : 0u;
-    g->global_hash = fallback || hl > 15;
+    g->global_hash = fallback || hl > 15 || env_int("RG_K1_GHASH", 0) != 0;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
     p.hash_log2 = hl;
     p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
@@ -506,7 +513,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.off_hash = off;
     if (!g->global_hash) off += (4u << hl);
     p.off_stage = off;
-    p.stage_bufs = ix->cfg_stage_bufs ? uint32_t(ix->cfg_stage_bufs) : 2u;
+    p.stage_bufs = ix->cfg_stage_bufs ? uint32_t(ix->cfg_stage_bufs) : uint32_t(env_int("RG_K1_BUFS", 2));
     if (g->gather != 3) off += round_up(p.stage_bufs * br * rs * 4, 128);
     p.off_mbar = off;
     off += 128;
