@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=2000, help="queries timed on the CPU baseline")
     ap.add_argument("--gather", type=int, default=0)
     ap.add_argument("--stage-rows", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0, help="warps per query (0 = library default)")
+    ap.add_argument("--hash-space", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -202,7 +204,7 @@ def run_ours(args):
     d = prepare(args, rank, world, device)
     nq, k, dim = args.queries, args.k, args.dim
     ix = capi.Index(d["base"], d["offsets"], d["adj"], d["ep"], metric=capi.METRIC_IP, device=local)
-    ix.configure(gather=args.gather, stage_rows=args.stage_rows)
+    ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
     dists = torch.empty((nq, k), dtype=torch.float32, device=device)

@@ -80,10 +80,12 @@ RG_API rg_status rg_search_batch(rg_index *index, const float *queries, uint64_t
 RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries, uint64_t nq, uint32_t k,
                                         uint32_t L, uint32_t *d_ids, float *d_dists, uint32_t *d_cmps,
                                         uint32_t *d_hops, uint32_t *d_status, void *cuda_stream);
-/* Tuning knobs (0 = automatic): see DESIGN.md "K1".  gather: 0 auto, 1 cp.async (LDGSTS),
- * 2 TMA bulk copy (cp.async.bulk + mbarrier). */
-RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_cta, int ctas_per_sm,
-                                     int stage_rows, int hash_log2);
+/* Tuning knobs (0 = automatic): see DESIGN.md "K1".  gather: 1 cp.async (LDGSTS), 2 TMA bulk copy (cp.async.bulk +
+ * mbarrier); warps_per_query: warps of the CTA that owns a query (1..8); stage_rows: rows per warp staging buffer. */
+RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
+                                     int hash_log2);
+/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA). */
+RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Number of kernel launches issued by this library on behalf of `index` so far. */
 RG_API uint64_t rg_index_launch_count(const rg_index *index);
 

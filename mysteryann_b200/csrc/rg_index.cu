@@ -180,29 +180,33 @@ rg_status rg_index_info(const rg_index *ix, uint64_t *n, uint32_t *dim, int *met
 
 uint64_t rg_index_launch_count(const rg_index *ix) { return ix ? ix->launches : 0; }
 
-rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_cta, int ctas_per_sm, int stage_rows,
+rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
                               int hash_log2) {
     if (!ix) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_configure: null index");
-    if (gather < 0 || gather > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "gather must be 0 (auto), 1 (cp.async), 2 (TMA bulk) or 3 (registers)");
-    if (warps_per_cta < 0 || warps_per_cta > 16 || ctas_per_sm < 0 || ctas_per_sm > 32)
-        return rg::fail(RG_ERR_INVALID_ARGUMENT, "warps_per_cta in [0,16], ctas_per_sm in [0,32]");
-    // stage_rows: multiple of 8 in [0,64]; +1 selects a single staging buffer instead of two (e.g. 9 = 8 rows, 1 buffer)
-    int stage_bufs = 0;
-    if (stage_rows % 8 == 1) {
-        stage_bufs = 1;
-        stage_rows -= 1;
-    }
+    if (gather < 0 || gather > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "gather must be 0 (auto), 1 (cp.async) or 2 (TMA bulk)");
+    if (warps_per_query < 0 || warps_per_query > 8 || ctas_per_sm < 0 || ctas_per_sm > 32)
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "warps_per_query in [0,8], ctas_per_sm in [0,32]");
     if (stage_rows < 0 || (stage_rows % 8) != 0 || stage_rows > 64)
-        return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_rows must be a multiple of 8 in [0,64] (+1 for a single buffer)");
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_rows must be a multiple of 8 in [0,64]");
     if (hash_log2 != 0 && (hash_log2 < 8 || hash_log2 > 22))
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_log2 must be 0 (auto) or in [8,22]");
     ix->cfg_gather = gather;
-    ix->cfg_warps = warps_per_cta;
+    ix->cfg_warps = warps_per_query;
     ix->cfg_ctas = ctas_per_sm;
     ix->cfg_stage_rows = stage_rows;
-    ix->cfg_stage_bufs = stage_bufs;
     ix->cfg_hash_log2 = hash_log2;
     return RG_OK;
 }
+
+rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
+    if (!ix || !name) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: null argument");
+    if (!strcmp(name, "hash_space")) {
+        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory) or 2 (global memory)");
+        ix->cfg_hash_space = value;
+        return RG_OK;
+    }
+    return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: unknown option '%s'", name);
+}
+
 
 }  // extern "C"

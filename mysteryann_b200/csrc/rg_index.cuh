@@ -25,7 +25,7 @@ struct rg_index {
     uint32_t *d_counters = nullptr;       // see rg_search.cu: kCounter*
     uint32_t *d_overflow_list = nullptr;  // query ids that overflowed the shared-memory visited set
     uint64_t overflow_cap = 0;
-    uint32_t *d_ghash = nullptr;  // global-memory visited-hash slabs (fallback / very large L)
+    uint32_t *d_ghash = nullptr;  // global-memory visited-hash slabs, one per resident CTA (L2-resident at the usual L)
     uint64_t ghash_words = 0;
 
     // staging for the host-buffer API
@@ -41,7 +41,7 @@ struct rg_index {
     cudaStream_t stream = nullptr;  // private stream of the host-buffer API
 
     // tuning (0 = auto)
-    int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0, cfg_stage_bufs = 0;
+    int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0, cfg_hash_space = 0;
 
     uint64_t launches = 0;
 };

@@ -2,19 +2,21 @@
 // /root/reference src/index_bipartite.cpp:2311-2420, and the OpenMP query loop of
 // tests/test_search_roargraph.cpp:203-209).
 //
-// One warp owns one query at a time; a persistent grid pulls query indices from an atomic counter
-// (the reference's schedule(dynamic,1)).  Per hop the warp
-//   1. pops the closest unexpanded pool entry              (NeighborPriorityQueue::closest_unexpanded)
-//   2. reads that node's fixed-stride adjacency row        (one dependent HBM read)
-//   3. filters the neighbours through an exact visited set (32-bit open-addressing hash in shared memory;
-//                                                           replaces VisitedList's uint16 tag array)
-//   4. gathers the surviving rows HBM -> shared memory     (TMA bulk copies on an mbarrier, or cp.async),
-//      double buffered in batches of `stage_rows`
-//   5. scores 8 rows at a time, 4 lanes per row, in the exact FP32 operation order of the compiled
-//      reference distance (16 lane accumulators, unfused main loop, fused tails; distance.h:39-89,179-223)
-//   6. merges the scored candidates into the sorted pool   (NeighborPriorityQueue::insert semantics)
-// Within a hop the order of insertion does not change the final pool (bounded sorted set under the
-// strict order (distance,id)), so steps 3-6 are batch operations with bit-identical results.
+// One CTA of W warps (W = 1..8, default 2) owns one query at a time; a persistent grid pulls query indices from an
+// atomic counter (the reference's schedule(dynamic,1)).  Per hop the CTA
+//   1. takes the closest unexpanded pool entry             (NeighborPriorityQueue::closest_unexpanded)
+//   2. reads that node's fixed-stride adjacency row, one word per thread (neighbour j belongs to warp j % W)
+//   3. filters the neighbours through an exact visited set (32-bit open-addressing hash, atomicCAS; by default an
+//      L2-resident slab per CTA in global memory, optionally shared memory; replaces VisitedList's uint16 tag array)
+//   4. every warp gathers the rows of ITS surviving neighbours HBM -> shared memory (TMA bulk copies on an mbarrier,
+//      or cp.async) in batches of `stage_rows`
+//   5. and scores them 8 rows at a time, 4 lanes per row, in the exact FP32 operation order of the compiled
+//      reference distance (16 lane accumulators, unfused main loop, fused tails; distance.h:39-89,179-223);
+//      keys that cannot enter the pool (>= its last entry once full) are dropped on the spot
+//   6. all threads merge the hop's candidates into the sorted pool in parallel (rank by counting + binary search,
+//      scatter into the second pool buffer) - same final state as NeighborPriorityQueue::insert one by one.
+// Within a hop the order of insertion does not change the final pool (bounded sorted set under the strict order
+// (distance,id)), so steps 2-6 are batch operations with bit-identical results, cmps and hops included.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +27,9 @@ namespace rg {
 
 enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4 };
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kMaxWarps = 8;
+// shared control words
+enum { kCtlWork = 0, kCtlNvis = 1, kCtlHop0 = 4 /* 2 x {ncand, ndup, minpos, curpos} */ };
 
 struct SearchParams {
     const float *base;
@@ -36,18 +41,17 @@ struct SearchParams {
     uint32_t *hops;
     uint32_t *counters;
     uint32_t *overflow_list;   // primary pass appends here; fallback pass reads from here
-    uint32_t *ghash;           // global visited-hash slabs (kGlobalHash only)
+    uint32_t *ghash;           // global visited-hash slabs, one per CTA (kGlobalHash only)
     uint32_t nq;               // primary: number of queries; fallback: unused (count read from counters)
     uint32_t dim, adj_stride, ep, k, L;
     uint32_t hash_log2, hash_limit;
-    uint32_t stage_rows;       // rows per staging buffer (multiple of 8)
-    uint32_t stage_bufs;       // 1 = single buffer (more resident warps), 2 = double buffered
+    uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
-    uint32_t cand_cap;         // capacity of the candidate arrays (>= adj_stride)
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
     uint32_t fallback;         // 1 = second pass over overflow_list with the big global table
-    // byte offsets inside the per-warp shared-memory slice
-    uint32_t smem_per_warp, off_pool, off_cid, off_ckey, off_hash, off_stage, off_mbar;
+    // byte offsets inside the CTA's shared memory
+    uint32_t off_pool0, off_pool1, off_cand, off_rank, off_ctrl, off_hash, off_warp;
+    uint32_t warp_bytes, woff_cid, woff_stage;  // per-warp area: [mbarrier][candidate ids][row staging]
 };
 
 // ---- exact visited set --------------------------------------------------------------------------
@@ -130,206 +134,104 @@ __device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ 
     return finish_distance<kIP>(acc, tail8, vt, qt, t);
 }
 
-__device__ __forceinline__ float4 ldg_stream(const float4 *p) {  // read-once row data: keep it out of L1
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
-}
 
-// row read straight from HBM into registers (gather mode 3): kChunk 128-bit loads per lane are in flight
-// before the first one is consumed
-template <bool kIP, int kChunk>
-__device__ __forceinline__ float lane_exact_distance_global(const float4 *__restrict__ gp,
-                                                             const float4 *__restrict__ qp, uint32_t n16, bool tail8,
-                                                             uint32_t t) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
-    if (tail8 && t < 2) vt = ldg_stream(gp + 4 * n16);
-    for (uint32_t s0 = 0; s0 < n16; s0 += kChunk) {
-        float4 v[kChunk];
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j)
-            if (s0 + j < n16) v[j] = ldg_stream(gp + 4 * (s0 + j));
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j)
-            if (s0 + j < n16) main_step<kIP>(acc, v[j], qp[4 * (s0 + j)]);
-    }
-    if (tail8 && t < 2) qt = qp[4 * n16];
-    return finish_distance<kIP>(acc, tail8, vt, qt, t);
-}
-
-// kGather: 1 = cp.async (LDGSTS 16 B per lane) into shared memory, 2 = TMA bulk copy (one UBLKCP per row) into shared
-// memory on an mbarrier, 3 = straight into registers (LDG.128, no staging buffer -> more resident warps)
+// kGather: 1 = cp.async (LDGSTS 16 B per lane), 2 = TMA bulk copy (one UBLKCP per row) on an mbarrier
 template <bool kIP, int kGather, bool kGlobalHash>
-__global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t tid = threadIdx.x, T = blockDim.x, W = T >> 5;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t grp = lane >> 2, t = lane & 3;
-    unsigned char *ws = smem_raw + size_t(warp) * p.smem_per_warp;
-    float *s_query = reinterpret_cast<float *>(ws);
-    uint64_t *s_pool = reinterpret_cast<uint64_t *>(ws + p.off_pool);
-    uint32_t *s_cid = reinterpret_cast<uint32_t *>(ws + p.off_cid);
-    uint64_t *s_ckey = reinterpret_cast<uint64_t *>(ws + p.off_ckey);
-    float *s_stage = reinterpret_cast<float *>(ws + p.off_stage);
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(ws + p.off_mbar);
-    uint32_t *hash = kGlobalHash
-                         ? p.ghash + ((size_t(blockIdx.x) * (blockDim.x >> 5) + warp) << p.hash_log2)
-                         : reinterpret_cast<uint32_t *>(ws + p.off_hash);
+    float *s_query = reinterpret_cast<float *>(smem_raw);
+    uint64_t *s_pool0 = reinterpret_cast<uint64_t *>(smem_raw + p.off_pool0);
+    uint64_t *s_pool1 = reinterpret_cast<uint64_t *>(smem_raw + p.off_pool1);
+    uint64_t *s_cand = reinterpret_cast<uint64_t *>(smem_raw + p.off_cand);
+    uint32_t *s_rank = reinterpret_cast<uint32_t *>(smem_raw + p.off_rank);
+    volatile uint32_t *s_ctrl = reinterpret_cast<volatile uint32_t *>(smem_raw + p.off_ctrl);
+    uint32_t *s_ctrl_nv = reinterpret_cast<uint32_t *>(smem_raw + p.off_ctrl);
+    unsigned char *wa = smem_raw + p.off_warp + size_t(warp) * p.warp_bytes;
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);
+    uint32_t *s_cid = reinterpret_cast<uint32_t *>(wa + p.woff_cid);
+    float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
+    uint32_t *hash = kGlobalHash ? p.ghash + (size_t(blockIdx.x) << p.hash_log2)
+                                 : reinterpret_cast<uint32_t *>(smem_raw + p.off_hash);
 
     const uint32_t dim = p.dim, n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
     const uint32_t cpr = dim >> 2;  // 16-byte chunks per row
     const uint32_t L = p.L, BR = p.stage_rows, RS = p.row_stride;
-    uint32_t phase_bits = 0;  // mbarrier parity of the two staging buffers
+    uint32_t mb_phase = 0;
 
     if (kGather == 2) {
         if (lane == 0) {
-            mbar_init(&s_mbar[0], 1);
-            mbar_init(&s_mbar[1], 1);
+            mbar_init(s_mbar, 1);
             fence_mbar_init();
         }
-        __syncwarp();
     }
+    __syncthreads();
 
-    // ---- gather helpers: stage candidate rows [c0, c0 + rows) into buffer `buf` ------------------
-    auto issue = [&](uint32_t c0, uint32_t rows, uint32_t buf) {
-        float *dst0 = s_stage + size_t(buf) * BR * RS;
-        if (kGather == 2) {
-            if (lane == 0) mbar_arrive_expect_tx(&s_mbar[buf], rows * dim * 4u);
-            __syncwarp();
-            for (uint32_t r = lane; r < rows; r += 32) {
-                const uint32_t id = s_cid[c0 + r];
-                bulk_g2s(dst0 + size_t(r) * RS, p.base + size_t(id) * dim, dim * 4u, &s_mbar[buf]);
-            }
-        } else {
-            const uint32_t total = rows * cpr;
-            for (uint32_t idx = lane; idx < total; idx += 32) {
-                const uint32_t r = __umulhi(idx, p.chunk_magic);
-                const uint32_t c = idx - r * cpr;
-                const uint32_t id = s_cid[c0 + r];
-                cp_async16(dst0 + size_t(r) * RS + 4 * c, p.base + size_t(id) * dim + 4 * c);
-            }
-            cp_async_commit();
-        }
-    };
-    auto wait_buf = [&](uint32_t buf, bool another_in_flight) {
-        if (kGather == 2) {
-            mbar_wait(&s_mbar[buf], (phase_bits >> buf) & 1u);
-            phase_bits ^= (1u << buf);
-        } else {
-            if (another_in_flight) cp_async_wait<1>();
-            else cp_async_wait<0>();
-            __syncwarp();
-        }
-    };
-    // scores s_cid[0..ncand) -> s_ckey[0..ncand)
-    auto score = [&](uint32_t ncand) {
-        if (kGather == 3) {
-            const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
-            for (uint32_t r0 = 0; r0 < ncand; r0 += 8) {
-                const uint32_t r = r0 + grp;
-                const bool valid = r < ncand;
-                const uint32_t id = s_cid[valid ? r : ncand - 1];
-                const float4 *gp = reinterpret_cast<const float4 *>(p.base + size_t(id) * dim) + t;
-                const float d = lane_exact_distance_global<kIP, 8>(gp, qp, n16, tail8, t);
-                if (valid && t == 0) s_ckey[r] = make_key(d, id);
-            }
-            __syncwarp();
-            return;
-        }
-        const uint32_t nb = (ncand + BR - 1) / BR;
-        if (p.stage_bufs == 1) {  // overlap comes from the other resident warps
-            for (uint32_t b = 0; b < nb; ++b) {
-                const uint32_t c0 = b * BR;
-                const uint32_t rows = min(BR, ncand - c0);
-                issue(c0, rows, 0);
-                wait_buf(0, false);
-                for (uint32_t r0 = 0; r0 < rows; r0 += 8) {
-                    const uint32_t r = r0 + grp;
-                    const bool valid = r < rows;
-                    const uint32_t rr = valid ? r : rows - 1;
-                    const float4 *rp = reinterpret_cast<const float4 *>(s_stage + size_t(rr) * RS) + t;
-                    const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
-                    const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
-                    if (valid && t == 0) s_ckey[c0 + r] = make_key(d, s_cid[c0 + r]);
+    // Gathers and scores this warp's candidates s_cid[0..n); keys below `tail` are appended to the CTA-wide list.
+    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl) {
+        for (uint32_t c0 = 0; c0 < n; c0 += BR) {
+            const uint32_t rows = min(BR, n - c0);
+            if (kGather == 2) {
+                if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
+                __syncwarp();
+                for (uint32_t r = lane; r < rows; r += 32)
+                    bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
+                mbar_wait(s_mbar, mb_phase);
+                mb_phase ^= 1u;
+            } else {
+                const uint32_t total = rows * cpr;
+                for (uint32_t idx = lane; idx < total; idx += 32) {
+                    const uint32_t r = __umulhi(idx, p.chunk_magic);
+                    const uint32_t c = idx - r * cpr;
+                    cp_async16(s_stage + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
                 }
+                cp_async_commit();
+                cp_async_wait<0>();
                 __syncwarp();
             }
-            return;
-        }
-        issue(0, min(BR, ncand), 0);
-        for (uint32_t b = 0; b < nb; ++b) {
-            const uint32_t c0 = b * BR;
-            const uint32_t rows = min(BR, ncand - c0);
-            const bool more = (b + 1 < nb);
-            if (more) issue(c0 + BR, min(BR, ncand - c0 - BR), (b + 1) & 1);
-            wait_buf(b & 1, more);
-            const float *buf0 = s_stage + size_t(b & 1) * BR * RS;
             for (uint32_t r0 = 0; r0 < rows; r0 += 8) {
                 const uint32_t r = r0 + grp;
                 const bool valid = r < rows;
                 const uint32_t rr = valid ? r : rows - 1;
-                const float4 *rp = reinterpret_cast<const float4 *>(buf0 + size_t(rr) * RS) + t;
+                const float4 *rp = reinterpret_cast<const float4 *>(s_stage + size_t(rr) * RS) + t;
                 const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
                 const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
-                if (valid && t == 0) s_ckey[c0 + r] = make_key(d, s_cid[c0 + r]);
+                const uint64_t key = make_key(d, s_cid[c0 + rr]);
+                // NeighborPriorityQueue::insert rejects keys behind the last entry of a full pool (neighbor.h:151);
+                // the tail only tightens during a hop, so dropping them here is exact
+                const bool keep = valid && t == 0 && key < tail;
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    const uint32_t leader = __ffs(m) - 1;
+                    uint32_t pos0 = 0;
+                    if (lane == leader) pos0 = atomicAdd(&s_ctrl_nv[ctl], uint32_t(__popc(m)));
+                    pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+                    if (keep) s_cand[pos0 + __popc(m & lanemask_lt())] = key;
+                }
             }
-            __syncwarp();  // all reads of this buffer done before it is refilled two batches later
-        }
-    };
-
-    uint32_t size = 0, cur = 0;
-    uint64_t tail = ~0ull;  // (distance,id) of the last entry once the pool is full, else +inf (warp-uniform)
-    // NeighborPriorityQueue::insert (neighbor.h:150-183) for one key, executed by the whole warp
-    auto pool_insert = [&](uint64_t key) {
-        if (key >= tail) return;  // full pool and worse than its last entry, or the very same (distance,id)
-        uint32_t pos = 0;
-        bool dup = false;
-        for (uint32_t i0 = 0; i0 < size; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const uint64_t e = (i < size) ? s_pool[i] : ~0ull;
-            pos += __popc(__ballot_sync(0xffffffffu, e < key));
-            dup |= __any_sync(0xffffffffu, (e & ~1ull) == key);
-        }
-        if (dup) return;  // "Make sure the same id isn't inserted into the set" (neighbor.h:161)
-        const int last = (size < L) ? int(size) : int(L) - 1;  // highest index written by the shift
-        for (int hi = last; hi > int(pos); hi -= 32) {
-            const int i = hi - int(lane);
-            uint64_t v = 0;
-            if (i > int(pos)) v = s_pool[i - 1];
-            __syncwarp();
-            if (i > int(pos)) s_pool[i] = v;
-            __syncwarp();
-        }
-        if (lane == 0) s_pool[pos] = key;
-        __syncwarp();
-        if (size < L) ++size;
-        if (pos < cur) cur = pos;
-        if (size == L) tail = s_pool[L - 1] & ~1ull;
-    };
-    // all scored candidates of a hop: lanes test their keys against the tail in parallel, survivors are inserted
-    // one by one (the tail only tightens, so a key rejected here would be rejected by insert() as well)
-    auto merge = [&](uint32_t ncand) {
-        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
-            const uint64_t key = (c0 + lane < ncand) ? s_ckey[c0 + lane] : ~0ull;
-            uint32_t m = __ballot_sync(0xffffffffu, key < tail);
-            while (m) {
-                const uint32_t b = __ffs(m) - 1;
-                pool_insert(__shfl_sync(0xffffffffu, key, b));
-                m &= m - 1;
-                m &= __ballot_sync(0xffffffffu, key < tail);
-            }
+            __syncwarp();  // all reads of the staging buffer done before the next batch lands in it
         }
     };
 
     for (;;) {
         // ---- next query (schedule(dynamic,1)) ---------------------------------------------------
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(&p.counters[p.fallback ? kCntWork2 : kCntWork], 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
+        if (tid == 0) {
+            s_ctrl[kCtlWork] = atomicAdd(&p.counters[p.fallback ? kCntWork2 : kCntWork], 1u);
+            s_ctrl[kCtlNvis] = 0;
+            s_ctrl[kCtlHop0 + 0] = 0;  // ncand
+            s_ctrl[kCtlHop0 + 1] = 0;  // ndup
+            s_ctrl[kCtlHop0 + 2] = L;  // minpos
+            s_ctrl[kCtlHop0 + 3] = L;  // curpos
+            s_ctrl[kCtlHop0 + 4] = 0;
+            s_ctrl[kCtlHop0 + 5] = 0;
+            s_ctrl[kCtlHop0 + 6] = L;
+            s_ctrl[kCtlHop0 + 7] = L;
+        }
+        __syncthreads();
+        const uint32_t w = s_ctrl[kCtlWork];
         const uint32_t nwork = p.fallback ? min(p.counters[kCntOverflow], p.nq) : p.nq;
         if (w >= nwork) break;
         const uint32_t qi = p.fallback ? p.overflow_list[w] : w;
@@ -337,37 +239,107 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
         {   // query -> shared memory; clear the visited set
             const float4 *src = reinterpret_cast<const float4 *>(p.queries + size_t(qi) * dim);
             float4 *dst = reinterpret_cast<float4 *>(s_query);
-            for (uint32_t i = lane; i < cpr; i += 32) dst[i] = src[i];
+            for (uint32_t i = tid; i < cpr; i += T) dst[i] = src[i];
             uint4 *h4 = reinterpret_cast<uint4 *>(hash);
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            for (uint32_t i = lane; i < (1u << (p.hash_log2 - 2)); i += 32) h4[i] = e4;
+            for (uint32_t i = tid; i < (1u << (p.hash_log2 - 2)); i += T) h4[i] = e4;
         }
-        __syncwarp();
+        __syncthreads();
 
-        size = 0;
-        cur = 0;
-        tail = ~0ull;
-        uint32_t cmps = 0, hops = 0, nvis = 0;
-        bool overflow = false;
+        uint32_t size = 0, cur = 0, hops = 0, nvis = 0, hp = 0;  // hp: parity of the hop's control words
+        uint64_t tail = ~0ull;  // (distance,id) of the last entry once the pool is full, else +inf
+        uint64_t *P = s_pool0, *N = s_pool1;
+        bool have_cur = false, overflow = false;
 
         // entry point: scored and inserted, NOT marked visited (src/index_bipartite.cpp:2337-2353)
-        if (lane == 0) s_cid[0] = p.ep;
-        __syncwarp();
-        score(1);
-        pool_insert(s_ckey[0]);
-
-        while (cur < size) {
-            // closest_unexpanded (neighbor.h:185-192)
-            const uint64_t ckey = s_pool[cur];
-            const uint32_t cur_id = key_id(ckey);
-            if (lane == 0) s_pool[cur] = ckey | 1ull;
+        if (warp == 0) {
+            if (lane == 0) s_cid[0] = p.ep;
             __syncwarp();
-            {
-                uint32_t c = cur + 1;
-                uint32_t next = size;
+            gather_and_score(1, tail, kCtlHop0);
+        }
+
+        for (;;) {
+            __syncthreads();  // the hop's candidates are in s_cand
+            const uint32_t ctl = kCtlHop0 + 4 * hp, octl = kCtlHop0 + 4 * (hp ^ 1u);  // this hop's / the other hop's words
+            const uint32_t C = s_ctrl[ctl + 0];
+            nvis = s_ctrl[kCtlNvis];
+            uint32_t start;
+            if (C == 0) {
+                // nothing to insert: flag the expanded entry (closest_unexpanded, neighbor.h:185-192)
+                if (tid == 0) {
+                    P[cur] |= 1ull;
+                    s_ctrl[octl + 0] = 0;
+                    s_ctrl[octl + 1] = 0;
+                    s_ctrl[octl + 2] = L;
+                    s_ctrl[octl + 3] = L;
+                }
+                __syncthreads();
+                start = cur + 1;
+            } else {
+                // (a) position of every candidate among the pool entries; a candidate equal to a pool entry is the
+                //     re-scored entry point: "Make sure the same id isn't inserted into the set" (neighbor.h:161)
+                for (uint32_t j = tid; j < C; j += T) {
+                    const uint64_t key = s_cand[j];
+                    uint32_t lo = 0, hi = size;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((P[mid] & ~1ull) < key) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    if (lo < size && (P[lo] & ~1ull) == key) {
+                        s_cand[j] = ~0ull;
+                        atomicAdd(&s_ctrl_nv[ctl + 1], 1u);
+                    } else {
+                        s_rank[j] = lo;
+                    }
+                }
+                if (tid == 0) {  // the other hop's control words are free again
+                    s_ctrl[octl + 0] = 0;
+                    s_ctrl[octl + 1] = 0;
+                    s_ctrl[octl + 2] = L;
+                    s_ctrl[octl + 3] = L;
+                }
+                __syncthreads();
+                const uint32_t ndup = s_ctrl[ctl + 1];
+                // (b) candidates -> new pool
+                for (uint32_t j = tid; j < C; j += T) {
+                    const uint64_t key = s_cand[j];
+                    if (key == ~0ull) continue;
+                    uint32_t r = 0;
+                    for (uint32_t i = 0; i < C; ++i) r += (s_cand[i] < key) ? 1u : 0u;
+                    const uint32_t pos = s_rank[j] + r;
+                    if (pos < L) {
+                        N[pos] = key;
+                        atomicMin(&s_ctrl_nv[ctl + 2], pos);
+                    }
+                }
+                // (c) old entries shift right by the number of candidates in front of them
+                for (uint32_t i = tid; i < size; i += T) {
+                    uint64_t e = P[i];
+                    const uint64_t ek = e & ~1ull;
+                    uint32_t sh = 0;
+                    for (uint32_t j = 0; j < C; ++j) sh += (s_cand[j] < ek) ? 1u : 0u;
+                    const uint32_t pos = i + sh;
+                    if (have_cur && i == cur) {
+                        e |= 1ull;
+                        s_ctrl[ctl + 3] = pos;
+                    }
+                    if (pos < L) N[pos] = e;
+                }
+                __syncthreads();
+                size = min(L, size + C - ndup);
+                uint64_t *tmp = P;
+                P = N;
+                N = tmp;
+                const uint32_t minpos = s_ctrl[ctl + 2], curpos = s_ctrl[ctl + 3];
+                start = have_cur ? min(minpos, curpos + 1) : 0u;
+            }
+            hp ^= 1u;
+            {   // first unexpanded entry at or after `start` (everything in front of it is expanded)
+                uint32_t c = start, next = size;
                 while (c < size) {
                     const uint32_t i = c + lane;
-                    const bool unexp = (i < size) && ((s_pool[i] & 1ull) == 0);
+                    const bool unexp = (i < size) && ((P[i] & 1ull) == 0);
                     const uint32_t m = __ballot_sync(0xffffffffu, unexp);
                     if (m) {
                         next = c + (__ffs(m) - 1);
@@ -377,104 +349,114 @@ __global__ void __launch_bounds__(256) rg_search_kernel(const SearchParams p) {
                 }
                 cur = next;
             }
-            ++hops;
+            if (size == L) tail = P[L - 1] & ~1ull;
+            if (cur >= size) break;
 
+            // ---- expand P[cur] -------------------------------------------------------------------
+            have_cur = true;
+            const uint32_t cur_id = key_id(P[cur]);
+            ++hops;
             if (nvis + p.adj_stride > p.hash_limit) {  // visited set may fill up: hand over to the big-table pass
                 overflow = true;
                 break;
             }
-            // adjacency row, visited filter, compaction into s_cid (adjacency order preserved)
+            // adjacency row: neighbour j is handled by warp j % W, lane (j / W) % 32; the first three rounds are
+            // requested together with the degree word: one DRAM round trip
             const uint32_t *row = p.adj + size_t(cur_id) * p.adj_stride;
-            uint32_t ncand = 0;
-            uint32_t deg = 0;
-            uint32_t wreg[3];  // the whole row (<= 96 words) is requested at once: one DRAM round trip
+            uint32_t wreg[3];
 #pragma unroll
-            for (uint32_t c = 0; c < 3; ++c) {
-                const uint32_t idx = c * 32 + lane;
-                wreg[c] = (idx < p.adj_stride) ? __ldg(row + idx) : kEmpty;
+            for (uint32_t it = 0; it < 3; ++it) {
+                const uint32_t j = (lane + 32 * it) * W + warp;
+                wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
             }
-            for (uint32_t c0 = 0; c0 < p.adj_stride; c0 += 32) {
-                const uint32_t idx = c0 + lane;
+            const uint32_t deg = __ldg(row);
+            uint32_t n_w = 0;
+            for (uint32_t it = 0; it * 32 * W < deg; ++it) {
+                const uint32_t j = (lane + 32 * it) * W + warp;
                 uint32_t word;
-                if (c0 == 0) word = wreg[0];
-                else if (c0 == 32) word = wreg[1];
-                else if (c0 == 64) word = wreg[2];
-                else word = (idx < p.adj_stride) ? __ldg(row + idx) : kEmpty;
-                if (c0 == 0) deg = __shfl_sync(0xffffffffu, word, 0);
-                if (c0 > deg) break;  // warp-uniform
-                const bool is_nbr = (idx >= 1) && (idx <= deg);
+                if (it == 0) word = wreg[0];
+                else if (it == 1) word = wreg[1];
+                else if (it == 2) word = wreg[2];
+                else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
                 bool fresh = false;
-                if (is_nbr) fresh = visited_test_and_set(hash, p.hash_log2, word);
+                if (j < deg) fresh = visited_test_and_set(hash, p.hash_log2, word);
                 const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                if (fresh) s_cid[ncand + __popc(m & lanemask_lt())] = word;
-                ncand += __popc(m);
+                if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
+                n_w += __popc(m);
             }
             __syncwarp();
-            cmps += ncand;
-            nvis += ncand;
-            if (ncand == 0) continue;
-            score(ncand);
-            // a re-scored entry point lands here too; insert() drops it as a duplicate (neighbor.h:161) or as
-            // worse than the tail (neighbor.h:151), exactly like the reference
-            merge(ncand);
+            if (n_w) {
+                if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
+                // a re-scored entry point lands here too; the merge drops it as a duplicate (neighbor.h:161) or the tail
+                // test drops it (neighbor.h:151), exactly like the reference
+                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp);
+            }
         }
 
         if (overflow) {
             if (!p.fallback) {
-                if (lane == 0) {
+                if (tid == 0) {
                     const uint32_t pos = atomicAdd(&p.counters[kCntOverflow], 1u);
                     p.overflow_list[pos] = qi;
                 }
+                __syncthreads();
                 continue;
             }
-            if (lane == 0) atomicAdd(&p.counters[kCntFatal], 1u);
+            if (tid == 0) atomicAdd(&p.counters[kCntFatal], 1u);
             size = 0;  // falls through to the "not enough results" fill
         }
         // results (src/index_bipartite.cpp:2408-2419)
         if (size < p.k) {
-            if (lane == 0 && !overflow) atomicAdd(&p.counters[kCntNotEnough], 1u);
-            for (uint32_t i = lane; i < p.k; i += 32) {
+            if (tid == 0 && !overflow) atomicAdd(&p.counters[kCntNotEnough], 1u);
+            for (uint32_t i = tid; i < p.k; i += T) {
                 p.ids[size_t(qi) * p.k + i] = kEmpty;
                 p.dists[size_t(qi) * p.k + i] = 0.f;
             }
         } else {
-            for (uint32_t i = lane; i < p.k; i += 32) {
-                const uint64_t e = s_pool[i];
+            for (uint32_t i = tid; i < p.k; i += T) {
+                const uint64_t e = P[i];
                 p.ids[size_t(qi) * p.k + i] = key_id(e);
                 p.dists[size_t(qi) * p.k + i] = key_dist(e);
             }
         }
-        if (lane == 0) {
-            if (p.cmps) p.cmps[qi] = cmps;
+        if (tid == 0) {
+            if (p.cmps) p.cmps[qi] = nvis;
             if (p.hops) p.hops[qi] = hops;
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
 // ---- host side: geometry + launch ---------------------------------------------------------------
+typedef void (*SearchKernel)(const SearchParams);
+
 struct Geometry {
     SearchParams p;
-    int warps, ctas_per_sm, gather;
+    int warps, gather;
     bool global_hash;
     size_t smem_bytes;
+    SearchKernel fn;
+    int ctas_per_sm;
 };
 
 static uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-// experiment knobs (tuning sweeps only; 0 / unset = automatic)
-static int env_int(const char *name, int def) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : def;
-}
-
 static uint32_t auto_hash_log2(uint32_t L) {
     // expected worst-case visited nodes per query ~ 1000 + 30 L (max cmps 1371 @L=10 ...
-    // 13702 @L=500); outliers take the exact global-table fallback, so this only affects speed.
+    // 13702 @L=500); outliers take the exact big-table fallback pass, so this only affects speed.
     const double want = (1000.0 + 30.0 * L) / 0.8;
     uint32_t lg = 10;
     while ((1u << lg) < want && lg < 22) ++lg;
     return lg;
+}
+
+static SearchKernel pick_kernel(bool ip, int gather, bool gh) {
+    if (gather == 2) {
+        if (gh) return ip ? rg_search_kernel<true, 2, true> : rg_search_kernel<false, 2, true>;
+        return ip ? rg_search_kernel<true, 2, false> : rg_search_kernel<false, 2, false>;
+    }
+    if (gh) return ip ? rg_search_kernel<true, 1, true> : rg_search_kernel<false, 1, true>;
+    return ip ? rg_search_kernel<true, 1, false> : rg_search_kernel<false, 1, false>;
 }
 
 static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, Geometry *g) {
@@ -485,94 +467,55 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.ep = ix->ep;
     p.k = k;
     p.L = L;
-    p.cand_cap = round_up(ix->adj_stride, 32);
     const uint32_t cpr = ix->dim / 4;
     p.chunk_magic = uint32_t((0x100000000ull + cpr - 1) / cpr);
     // smallest rs >= dim with rs % 32 == 16: the two rows a quarter-warp reads with LDS.128 fall in
     // different halves of the 32 banks
-    uint32_t rs = (ix->dim % 32 <= 16) ? ix->dim - ix->dim % 32 + 16 : ix->dim - ix->dim % 32 + 48;
-    p.row_stride = rs;
-    uint32_t br = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;  // 8 rows x 2 buffers measured best (profiles/)
-    p.stage_rows = br;
+    p.row_stride = (ix->dim % 32 <= 16) ? ix->dim - ix->dim % 32 + 16 : ix->dim - ix->dim % 32 + 48;
+    p.stage_rows = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
+    g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
+    const uint32_t W = uint32_t(g->warps);
 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L);
     p.fallback = fallback ? 1u : 0u;
-    g->global_hash = fallback || hl > 15 || env_int("RG_K1_GHASH", 0) != 0;
+    // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
+    g->global_hash = fallback || hl > 15 || ix->cfg_hash_space != 1;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
     p.hash_log2 = hl;
     p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
 
     uint32_t off = round_up(ix->dim * 4, 128);
-    p.off_pool = off;
+    p.off_pool0 = off;
     off += round_up((L + 1) * 8, 128);
-    p.off_cid = off;
-    off += round_up(p.cand_cap * 4, 128);
-    p.off_ckey = off;
-    off += round_up(p.cand_cap * 8, 128);
+    p.off_pool1 = off;
+    off += round_up((L + 1) * 8, 128);
+    p.off_cand = off;
+    off += round_up(ix->adj_stride * 8, 128);
+    p.off_rank = off;
+    off += round_up(ix->adj_stride * 4, 128);
+    p.off_ctrl = off;
+    off += 128;
     p.off_hash = off;
     if (!g->global_hash) off += (4u << hl);
-    p.off_stage = off;
-    p.stage_bufs = ix->cfg_stage_bufs ? uint32_t(ix->cfg_stage_bufs) : uint32_t(env_int("RG_K1_BUFS", 2));
-    if (g->gather != 3) off += round_up(p.stage_bufs * br * rs * 4, 128);
-    p.off_mbar = off;
-    off += 128;
-    p.smem_per_warp = off;
-
-    const size_t sm_budget = 227 * 1024, cta_overhead = 1024;
+    p.off_warp = off;
+    const uint32_t cid_cap = round_up((ix->adj_stride - 1 + W - 1) / W, 8);
+    p.woff_cid = 16;
+    p.woff_stage = round_up(16 + cid_cap * 4, 128);
+    p.warp_bytes = p.woff_stage + round_up(p.stage_rows * p.row_stride * 4, 128);
+    off += W * p.warp_bytes;
+    g->smem_bytes = off;
     if (size_t(off) > size_t(ix->max_smem_optin))
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u needs %u bytes of shared memory per query (max %d)", L, off,
                         ix->max_smem_optin);
-    int best_w = 1, best_c = 1, best_res = 0;
-    const int w_opts[] = {8, 4, 2, 1};
-    for (int w : w_opts) {
-        if (fallback && w > 2) continue;  // few heavy queries, big global tables: keep the slab count small
-        if (!fallback && ix->cfg_warps && w != ix->cfg_warps) continue;
-        const size_t cta = size_t(w) * off;
-        if (cta > size_t(ix->max_smem_optin)) continue;
-        int c = int(sm_budget / (cta + cta_overhead));
-        c = std::min(c, 2048 / (w * 32));
-        c = std::min(c, 32);
-        if (ix->cfg_ctas) c = std::min(c, ix->cfg_ctas);
-        if (c < 1) continue;
-        if (w * c > best_res) {
-            best_res = w * c;
-            best_w = w;
-            best_c = c;
-        }
-    }
-    if (!fallback && ix->cfg_warps && best_res == 0) {
-        best_w = ix->cfg_warps;
-        best_c = 1;
-        if (size_t(best_w) * off > size_t(ix->max_smem_optin))
-            return rg::fail(RG_ERR_INVALID_ARGUMENT, "warps_per_cta=%d does not fit in shared memory at L_pq=%u", best_w, L);
-    }
-    g->warps = best_w;
-    g->ctas_per_sm = best_c;
-    g->smem_bytes = size_t(best_w) * off;
+    g->fn = pick_kernel(ix->metric != RG_METRIC_L2, g->gather, g->global_hash);
+    cudaError_t e = cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(g->smem_bytes));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, g->fn, g->warps * 32, g->smem_bytes);
+    if (e != cudaSuccess) return rg::fail(RG_ERR_CUDA, "K1 launch configuration failed: %s", cudaGetErrorString(e));
+    if (g->ctas_per_sm < 1) return rg::fail(RG_ERR_INTERNAL, "K1 does not fit on an SM (L_pq=%u)", L);
+    if (ix->cfg_ctas) g->ctas_per_sm = std::min(g->ctas_per_sm, ix->cfg_ctas);
+    if (fallback) g->ctas_per_sm = 1;  // few heavy queries, big global tables: keep the slab count small
     return RG_OK;
-}
-
-template <bool kIP, int kGather, bool kGlobalHash>
-static cudaError_t launch_one(const Geometry &g, int grid, cudaStream_t st) {
-    auto kern = rg_search_kernel<kIP, kGather, kGlobalHash>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(g.smem_bytes));
-    if (e != cudaSuccess) return e;
-    kern<<<grid, g.warps * 32, g.smem_bytes, st>>>(g.p);
-    return cudaGetLastError();
-}
-
-static cudaError_t launch(const Geometry &g, bool ip, int grid, cudaStream_t st) {
-    if (g.gather == 3) {
-        if (g.global_hash) return ip ? launch_one<true, 3, true>(g, grid, st) : launch_one<false, 3, true>(g, grid, st);
-        return ip ? launch_one<true, 3, false>(g, grid, st) : launch_one<false, 3, false>(g, grid, st);
-    }
-    if (g.global_hash) {
-        if (g.gather == 2) return ip ? launch_one<true, 2, true>(g, grid, st) : launch_one<false, 2, true>(g, grid, st);
-        return ip ? launch_one<true, 1, true>(g, grid, st) : launch_one<false, 1, true>(g, grid, st);
-    }
-    if (g.gather == 2) return ip ? launch_one<true, 2, false>(g, grid, st) : launch_one<false, 2, false>(g, grid, st);
-    return ip ? launch_one<true, 1, false>(g, grid, st) : launch_one<false, 1, false>(g, grid, st);
 }
 
 static rg_status ensure(void **ptr, uint64_t *cap, uint64_t want, size_t elem) {
@@ -590,7 +533,7 @@ static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq
                                uint32_t *d_status, cudaStream_t st) {
     if (!ix || !d_queries || !d_ids || !d_dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search: null argument");
     if (k == 0 || L == 0 || k > L) return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq must greater or equal than k (k=%u, L_pq=%u)", k, L);
-    if (L > 16384) return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u too large (max 16384)", L);
+    if (L > 8192) return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u too large (max 8192)", L);
     if (nq >= (1ull << 32)) return rg::fail(RG_ERR_INVALID_ARGUMENT, "too many queries in one batch");
     if (nq == 0) return RG_OK;
 
@@ -599,16 +542,14 @@ static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq
     if (s != RG_OK) return s;
     s = make_geometry(ix, k, L, true, &g2);
     if (s != RG_OK) return s;
-    const bool ip = ix->metric != RG_METRIC_L2;
 
-    // scratch: overflow list (one slot per query) and global hash slabs
+    // scratch: overflow list (one slot per query) and global hash slabs (one per CTA)
     s = ensure((void **)&ix->d_overflow_list, &ix->overflow_cap, nq, sizeof(uint32_t));
     if (s != RG_OK) return s;
-    const int grid1 = int(std::min<uint64_t>((nq + g1.warps - 1) / g1.warps, uint64_t(ix->sm_count) * g1.ctas_per_sm));
-    // fallback pass: few, heavy queries; one CTA per SM
-    const int grid2 = ix->sm_count;
-    uint64_t need_hash = uint64_t(grid2) * g2.warps << g2.p.hash_log2;
-    if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1) * g1.warps << g1.p.hash_log2);
+    const int grid1 = int(std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm));
+    const int grid2 = ix->sm_count;  // fallback pass: few, heavy queries; one CTA per SM
+    uint64_t need_hash = uint64_t(grid2) << g2.p.hash_log2;
+    if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1) << g1.p.hash_log2);
     s = ensure((void **)&ix->d_ghash, &ix->ghash_words, need_hash, sizeof(uint32_t));
     if (s != RG_OK) return s;
 
@@ -626,9 +567,11 @@ static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq
         g->p.nq = uint32_t(nq);
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
-    RG_CUDA_OK(launch(g1, ip, grid1, st));
+    g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
+    RG_CUDA_OK(cudaGetLastError());
     ix->launches++;
-    RG_CUDA_OK(launch(g2, ip, grid2, st));  // exits immediately when nothing overflowed
+    g2.fn<<<grid2, g2.warps * 32, g2.smem_bytes, st>>>(g2.p);  // exits immediately when nothing overflowed
+    RG_CUDA_OK(cudaGetLastError());
     ix->launches++;
     if (d_status) {
         RG_CUDA_OK(cudaMemcpyAsync(d_status, ix->d_counters + kCntNotEnough, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

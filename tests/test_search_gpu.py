@@ -39,18 +39,22 @@ def capi():
     return capi
 
 
-@pytest.mark.parametrize("gather", (1, 2, 3))
+# (gather, warps per query, visited-hash space): cp.async / TMA bulk gathers, 1..8 warps per query, shared / global hash
+CONFIGS = ((2, 4, 2), (1, 4, 2), (2, 1, 1), (2, 2, 2), (1, 3, 1), (2, 8, 2))
+
+
+@pytest.mark.parametrize("gather,warps,space", CONFIGS)
 @pytest.mark.parametrize("name", CASES)
-def test_golden(capi, name, gather):
+def test_golden(capi, name, gather, warps, space):
     c = load_case(name)
     ix = capi.Index(c["base"], c["offsets"], c["adj"], c["ep"], metric=c["metric"])
-    ix.configure(gather=gather)
+    ix.configure(gather=gather, warps_per_query=warps, hash_space=space)
     for L in c["Ls"]:
         L = int(L)
         got = ix.search(c["test"], 10, L)
         assert got["rc"] == 0
         want = {k: c[f"{k}_{L}"] for k in ("ids", "dists", "cmps", "hops")}
-        report(f"{name} L={L} gather={gather}", got, want)
+        report(f"{name} L={L} gather={gather} warps={warps} space={space}", got, want)
     ix.close()
 
 
@@ -76,29 +80,30 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     if off[ep + 1] == off[ep]:
         ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    for gather in (1, 2, 3):
-        ix.configure(gather=gather)
+    for gather, warps, space in CONFIGS[:4]:
+        ix.configure(gather=gather, warps_per_query=warps, hash_space=space)
         for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
             want = oracle.search(base, off, adj, ep, q, k, L, metric=metric)
             got = ix.search(q, k, L)
             assert got["rc"] == want["rc"] == 0
-            report(f"dim={dim} metric={metric} gather={gather} L={L}", got, want)
+            report(f"dim={dim} metric={metric} gather={gather} warps={warps} space={space} L={L}", got, want)
     ix.close()
 
 
 def test_visited_overflow_takes_exact_fallback(capi, oracle):
-    """A tiny shared-memory hash forces most queries through the global-table pass; results stay exact."""
+    """A tiny visited hash forces most queries through the big-table pass; results stay exact."""
     rng = np.random.default_rng(5)
     n, dim = 30000, 40
     base = rng.standard_normal((n, dim)).astype(np.float32)
     q = rng.standard_normal((200, dim)).astype(np.float32)
     off, adj = random_graph(rng, n, 20, 60)
     ix = capi.Index(base, off, adj, 3, metric=1)
-    ix.configure(hash_log2=8)
     want = oracle.search(base, off, adj, 3, q, 10, 50, metric=1)
     assert want["cmps"].max() > 256
-    report("overflow", ix.search(q, 10, 50), want)
-    ix.configure(hash_log2=16)   # > 15: the primary pass itself uses global-memory tables
+    for space in (1, 2):
+        ix.configure(hash_log2=8, hash_space=space)
+        report(f"overflow space={space}", ix.search(q, 10, 50), want)
+    ix.configure(hash_log2=16, hash_space=1)   # > 15: too big for shared memory, global tables are used anyway
     report("global-primary", ix.search(q, 10, 50), want)
     ix.close()
 
@@ -114,7 +119,9 @@ def test_large_L_and_ties(capi, oracle):
         ix = capi.Index(base, off, adj, 1, metric=metric)
         for L in (10, 100, 500, 2000):
             want = oracle.search(base, off, adj, 1, q, 10, L, metric=metric)
-            report(f"ties metric={metric} L={L}", ix.search(q, 10, L), want)
+            for warps in (4, 1):
+                ix.configure(warps_per_query=warps)
+                report(f"ties metric={metric} L={L} warps={warps}", ix.search(q, 10, L), want)
         ix.close()
 
 
