@@ -112,6 +112,31 @@ RG_API rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_
  * failed the completeness certificate and were redone by the exact FP32 scan. */
 RG_API void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans);
 
+/* ---- graph construction on the GPU (build time) ---------------------------------------------------
+ * Replaces the CPU phases of IndexBipartite::BuildRoarGraph (src/index_bipartite.cpp:143-233) and LinkProjection
+ * (:1043-1277): entry point (:2004-2041), pivot projection + PruneBiSearchBaseGetBase (:1059-1097, 1612-1694),
+ * reverse edges (:1391-1432, 1527-1610), connectivity enhancement = L_pjpq beam searches from every base point
+ * (:1192-1220, 1279-1350) + PruneProjectionBaseSearchCandidates (:1846-1940) + supply reverse edges (:1352-1389),
+ * degree check (:1224-1248) and the final merge (:1251-1269).  Same pruning rules, applied per phase to all
+ * nodes at once (waves for the searches); like a multi-threaded reference build the adjacency is not
+ * edge-identical to the one-thread build.  d_knn_ids: the learn->base kNN ids [n_train][knn_k]
+ * (LoadLearnBaseKNN, :2622-2639; only the first M_sq per row are used).  All pointers are device memory. */
+typedef struct rg_graph rg_graph; /* device-resident fixed-stride adjacency + entry point */
+RG_API rg_status rg_build_roargraph_device(const float *d_base, uint64_t n, uint32_t dim, int metric,
+                                           const uint32_t *d_knn_ids, uint64_t n_train, uint32_t knn_k, uint32_t M_sq,
+                                           uint32_t M_pjbp, uint32_t L_pjpq, rg_graph **out, int device,
+                                           void *cuda_stream);
+/* phase_seconds (may be NULL): 6 doubles = entry point, projection, reverse edges, enhancement searches,
+ * enhancement prune + reverse edges, degree check + merge. */
+RG_API rg_status rg_graph_info(const rg_graph *graph, uint64_t *n, uint32_t *max_degree, uint64_t *nnz, uint32_t *ep,
+                               double *phase_seconds);
+/* CSR copy on the host for SaveProjectionGraph (:2606-2619): offsets[n+1], adj[nnz]. */
+RG_API rg_status rg_graph_download(const rg_graph *graph, uint64_t *offsets, uint32_t *adj);
+RG_API rg_status rg_graph_destroy(rg_graph *graph);
+/* Search index over a graph built on the device; d_base is adopted without copying (must outlive the index). */
+RG_API rg_status rg_index_create_from_graph(rg_index **out, const float *d_base, uint64_t n, uint32_t dim, int metric,
+                                            const rg_graph *graph);
+
 #ifdef __cplusplus
 }
 #endif

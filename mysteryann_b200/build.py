@@ -8,7 +8,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libroargraph_b200.so")
-SOURCES = ["rg_index.cu", "rg_search.cu", "rg_knn.cu"]
+SOURCES = ["rg_index.cu", "rg_search.cu", "rg_knn.cu", "rg_build.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
          "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]

@@ -22,7 +22,8 @@ METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option",
            "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device",
-           "rg_knn_last_stats"]
+           "rg_knn_last_stats", "rg_build_roargraph_device", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
+           "rg_index_create_from_graph"]
 
 _lib = None
 
@@ -69,6 +70,16 @@ def lib():
     L.rg_knn_merge_device.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32, vp]
     L.rg_knn_last_stats.restype = None
     L.rg_knn_last_stats.argtypes = [vp, vp]
+    L.rg_build_roargraph_device.restype = i32
+    L.rg_build_roargraph_device.argtypes = [vp, u64, u32, i32, vp, u64, u32, u32, u32, u32, C.POINTER(vp), i32, vp]
+    L.rg_graph_info.restype = i32
+    L.rg_graph_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rg_graph_download.restype = i32
+    L.rg_graph_download.argtypes = [vp, vp, vp]
+    L.rg_graph_destroy.restype = i32
+    L.rg_graph_destroy.argtypes = [vp]
+    L.rg_index_create_from_graph.restype = i32
+    L.rg_index_create_from_graph.argtypes = [C.POINTER(vp), vp, u64, u32, i32, vp]
     _lib = L
     return L
 
@@ -88,6 +99,17 @@ def _hp(a):
 
 class Index:
     """Device-resident RoarGraph index (base rows + projection graph + entry point)."""
+
+    @classmethod
+    def from_graph(cls, d_base, graph, metric=METRIC_IP):
+        """Search index over a device-built Graph; d_base is the CUDA torch tensor the graph was built from."""
+        self = cls.__new__(cls)
+        n, dim = d_base.shape
+        h = C.c_void_p()
+        _check(lib().rg_index_create_from_graph(C.byref(h), d_base.data_ptr(), n, dim, metric, graph._h))
+        self._h, self._keep = h, d_base
+        self.n, self.dim, self.metric, self.device, self.ep = int(n), int(dim), metric, d_base.device.index or 0, graph.ep
+        return self
 
     def __init__(self, base, offsets, adj, ep, metric=METRIC_IP, device=0):
         """base: numpy float32 [n, dim] (copied to the device) or a CUDA torch tensor (adopted, kept alive)."""
@@ -149,6 +171,39 @@ class Index:
         p = lambda t: None if t is None else t.data_ptr()
         _check(lib().rg_search_batch_device(self._h, p(d_queries), nq, k, L, p(d_ids), p(d_dists), p(d_cmps),
                                             p(d_hops), p(d_status), stream))
+
+
+class Graph:
+    """RoarGraph built on the GPU (rg_build_roargraph_device): fixed-stride adjacency + entry point, device resident."""
+
+    def __init__(self, d_base, d_knn_ids, M_sq=100, M_pjbp=35, L_pjpq=500, metric=METRIC_IP, stream=None):
+        """d_base: CUDA float32 [n, dim]; d_knn_ids: CUDA int32/uint32 [n_train, K] learn->base nearest neighbours."""
+        n, dim = d_base.shape
+        n_train, K = d_knn_ids.shape
+        assert d_base.is_contiguous() and d_knn_ids.is_contiguous() and d_knn_ids.element_size() == 4
+        h = C.c_void_p()
+        _check(lib().rg_build_roargraph_device(d_base.data_ptr(), n, dim, metric, d_knn_ids.data_ptr(), n_train, K, M_sq,
+                                               M_pjbp, L_pjpq, C.byref(h), d_base.device.index or 0, stream))
+        self._h = h
+        n_, md, nnz, ep = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)
+        sec = (C.c_double * 6)()
+        _check(lib().rg_graph_info(h, C.byref(n_), C.byref(md), C.byref(nnz), C.byref(ep), sec))
+        self.n, self.max_degree, self.nnz, self.ep = n_.value, md.value, nnz.value, ep.value
+        self.phase_seconds = dict(zip(("ep", "projection", "reverse", "enh_search", "enh_prune", "merge"), list(sec)))
+
+    def download(self):
+        """-> (ep, offsets u64 [n+1], adj u32 [nnz]) on the host (the CSR the index file format stores)."""
+        off = np.empty(self.n + 1, np.uint64)
+        adj = np.empty(self.nnz, np.uint32)
+        _check(lib().rg_graph_download(self._h, _hp(off), _hp(adj)))
+        return self.ep, off, adj
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rg_graph_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def knn_exact(base, queries, K, metric=METRIC_IP, id_base=0, device=0):

@@ -120,6 +120,30 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+// one warp sorts P (a power of two) 64-bit keys in shared memory, ascending (bitonic network)
+__device__ __forceinline__ void warp_sort_u64(uint64_t *s, uint32_t P, uint32_t lane) {
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P; i += 32) {
+                const uint32_t x = i ^ j;
+                if (x > i) {
+                    const uint64_t a = s[i], b = s[x];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b) == asc) {
+                        s[i] = b;
+                        s[x] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__device__ __forceinline__ uint32_t pow2_at_least(uint32_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
 #endif  // __CUDACC__
 
 }  // namespace rg

@@ -1,0 +1,77 @@
+// FP32 distances in the exact operation order of the compiled reference (include/efanna2e/distance.h:39-89,
+// 179-223 as g++ -Ofast emits them: 16 lane accumulators, unfused vmulps+vaddps main loop, fused 8-wide tail,
+// folds 16->8->4, (x0+x1)+(x2+x3)).  Four CUDA lanes score one row; lane t owns AVX lanes 4t..4t+3.
+#pragma once
+#include "rg_common.cuh"
+
+namespace rg {
+
+// ---- distance of 8 rows per warp, 4 lanes per row, reference operation order ---------------------
+// Lane t (0..3) of a group owns AVX lanes 4t..4t+3 of the reference's 16-lane accumulator.
+template <bool kIP>
+__device__ __forceinline__ void main_step(float4 &acc, const float4 v, const float4 q) {  // vmulps + vaddps
+    if (kIP) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
+    } else {
+        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
+                    dw = __fsub_rn(v.w, q.w);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
+    }
+}
+template <bool kIP>
+__device__ __forceinline__ void fused_step(float4 &m, const float4 v, const float4 q) {  // vfmadd231ps
+    if (kIP) {
+        m.x = __fmaf_rn(v.x, q.x, m.x);
+        m.y = __fmaf_rn(v.y, q.y, m.y);
+        m.z = __fmaf_rn(v.z, q.z, m.z);
+        m.w = __fmaf_rn(v.w, q.w, m.w);
+    } else {
+        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
+                    dw = __fsub_rn(v.w, q.w);
+        m.x = __fmaf_rn(dx, dx, m.x);
+        m.y = __fmaf_rn(dy, dy, m.y);
+        m.z = __fmaf_rn(dz, dz, m.z);
+        m.w = __fmaf_rn(dw, dw, m.w);
+    }
+}
+// folds 16 -> 8 (AVX lane l+8 lives two CUDA lanes up), the fused 8-wide tail, 8 -> 4, (x0+x1)+(x2+x3)
+template <bool kIP>
+__device__ __forceinline__ float finish_distance(const float4 acc, bool tail8, const float4 vt, const float4 qt,
+                                                  uint32_t t) {
+    float4 m;
+    m.x = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.x, 2), acc.x);
+    m.y = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.y, 2), acc.y);
+    m.z = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.z, 2), acc.z);
+    m.w = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.w, 2), acc.w);
+    if (tail8 && t < 2) fused_step<kIP>(m, vt, qt);
+    float4 f;
+    f.x = __fadd_rn(__shfl_down_sync(0xffffffffu, m.x, 1), m.x);
+    f.y = __fadd_rn(__shfl_down_sync(0xffffffffu, m.y, 1), m.y);
+    f.z = __fadd_rn(__shfl_down_sync(0xffffffffu, m.z, 1), m.z);
+    f.w = __fadd_rn(__shfl_down_sync(0xffffffffu, m.w, 1), m.w);
+    const float r = __fadd_rn(__fadd_rn(f.x, f.y), __fadd_rn(f.z, f.w));
+    return kIP ? -r : r;
+}
+
+// row staged in shared memory (gather modes 1, 2)
+template <bool kIP>
+__device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ rp, const float4 *__restrict__ qp,
+                                                      uint32_t n16, bool tail8, uint32_t t) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (uint32_t s = 0; s < n16; ++s) main_step<kIP>(acc, rp[4 * s], qp[4 * s]);
+    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
+    if (tail8 && t < 2) {
+        vt = rp[4 * n16];
+        qt = qp[4 * n16];
+    }
+    return finish_distance<kIP>(acc, tail8, vt, qt, t);
+}
+
+}  // namespace rg

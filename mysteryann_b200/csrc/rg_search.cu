@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "rg_distance.cuh"
 #include "rg_index.cuh"
 
 namespace rg {
@@ -49,6 +50,11 @@ struct SearchParams {
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
     uint32_t fallback;         // 1 = second pass over overflow_list with the big global table
+    // build mode (kBuild, SearchProjectionGraphInternal src/index_bipartite.cpp:1279-1350): query w is base row
+    // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
+    uint32_t node_lo, exp_cap;
+    uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
+    uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
     uint32_t off_pool0, off_pool1, off_cand, off_rank, off_ctrl, off_hash, off_warp;
     uint32_t warp_bytes, woff_cid, woff_stage;  // per-warp area: [mbarrier][candidate ids][row staging]
@@ -66,77 +72,8 @@ __device__ __forceinline__ bool visited_test_and_set(uint32_t *table, uint32_t l
     }
 }
 
-// ---- distance of 8 rows per warp, 4 lanes per row, reference operation order ---------------------
-// Lane t (0..3) of a group owns AVX lanes 4t..4t+3 of the reference's 16-lane accumulator.
-template <bool kIP>
-__device__ __forceinline__ void main_step(float4 &acc, const float4 v, const float4 q) {  // vmulps + vaddps
-    if (kIP) {
-        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
-        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
-    } else {
-        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
-                    dw = __fsub_rn(v.w, q.w);
-        acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
-        acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
-    }
-}
-template <bool kIP>
-__device__ __forceinline__ void fused_step(float4 &m, const float4 v, const float4 q) {  // vfmadd231ps
-    if (kIP) {
-        m.x = __fmaf_rn(v.x, q.x, m.x);
-        m.y = __fmaf_rn(v.y, q.y, m.y);
-        m.z = __fmaf_rn(v.z, q.z, m.z);
-        m.w = __fmaf_rn(v.w, q.w, m.w);
-    } else {
-        const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z),
-                    dw = __fsub_rn(v.w, q.w);
-        m.x = __fmaf_rn(dx, dx, m.x);
-        m.y = __fmaf_rn(dy, dy, m.y);
-        m.z = __fmaf_rn(dz, dz, m.z);
-        m.w = __fmaf_rn(dw, dw, m.w);
-    }
-}
-// folds 16 -> 8 (AVX lane l+8 lives two CUDA lanes up), the fused 8-wide tail, 8 -> 4, (x0+x1)+(x2+x3)
-template <bool kIP>
-__device__ __forceinline__ float finish_distance(const float4 acc, bool tail8, const float4 vt, const float4 qt,
-                                                  uint32_t t) {
-    float4 m;
-    m.x = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.x, 2), acc.x);
-    m.y = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.y, 2), acc.y);
-    m.z = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.z, 2), acc.z);
-    m.w = __fadd_rn(__shfl_down_sync(0xffffffffu, acc.w, 2), acc.w);
-    if (tail8 && t < 2) fused_step<kIP>(m, vt, qt);
-    float4 f;
-    f.x = __fadd_rn(__shfl_down_sync(0xffffffffu, m.x, 1), m.x);
-    f.y = __fadd_rn(__shfl_down_sync(0xffffffffu, m.y, 1), m.y);
-    f.z = __fadd_rn(__shfl_down_sync(0xffffffffu, m.z, 1), m.z);
-    f.w = __fadd_rn(__shfl_down_sync(0xffffffffu, m.w, 1), m.w);
-    const float r = __fadd_rn(__fadd_rn(f.x, f.y), __fadd_rn(f.z, f.w));
-    return kIP ? -r : r;
-}
-
-// row staged in shared memory (gather modes 1, 2)
-template <bool kIP>
-__device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ rp, const float4 *__restrict__ qp,
-                                                      uint32_t n16, bool tail8, uint32_t t) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (uint32_t s = 0; s < n16; ++s) main_step<kIP>(acc, rp[4 * s], qp[4 * s]);
-    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
-    if (tail8 && t < 2) {
-        vt = rp[4 * n16];
-        qt = qp[4 * n16];
-    }
-    return finish_distance<kIP>(acc, tail8, vt, qt, t);
-}
-
-
 // kGather: 1 = cp.async (LDGSTS 16 B per lane), 2 = TMA bulk copy (one UBLKCP per row) on an mbarrier
-template <bool kIP, int kGather, bool kGlobalHash>
+template <bool kIP, int kGather, bool kGlobalHash, bool kBuild>
 __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, T = blockDim.x, W = T >> 5;
@@ -237,7 +174,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         const uint32_t qi = p.fallback ? p.overflow_list[w] : w;
 
         {   // query -> shared memory; clear the visited set
-            const float4 *src = reinterpret_cast<const float4 *>(p.queries + size_t(qi) * dim);
+            const float4 *src = reinterpret_cast<const float4 *>(kBuild ? p.base + (size_t(p.node_lo) + qi) * dim
+                                                                        : p.queries + size_t(qi) * dim);
             float4 *dst = reinterpret_cast<float4 *>(s_query);
             for (uint32_t i = tid; i < cpr; i += T) dst[i] = src[i];
             uint4 *h4 = reinterpret_cast<uint4 *>(hash);
@@ -251,9 +189,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         uint64_t *P = s_pool0, *N = s_pool1;
         bool have_cur = false, overflow = false;
 
-        // entry point: scored and inserted, NOT marked visited (src/index_bipartite.cpp:2337-2353)
+        // entry point: scored and inserted, NOT marked visited (src/index_bipartite.cpp:2337-2353); the build-time
+        // search does mark it (:1309)
+        const uint32_t self = p.node_lo + qi;
         if (warp == 0) {
-            if (lane == 0) s_cid[0] = p.ep;
+            if (lane == 0) {
+                s_cid[0] = p.ep;
+                if (kBuild) visited_test_and_set(hash, p.hash_log2, p.ep);
+            }
             __syncwarp();
             gather_and_score(1, tail, kCtlHop0);
         }
@@ -355,6 +298,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
             // ---- expand P[cur] -------------------------------------------------------------------
             have_cur = true;
             const uint32_t cur_id = key_id(P[cur]);
+            if (kBuild && tid == 0 && hops < p.exp_cap) p.exp_keys[size_t(qi) * p.exp_cap + hops] = P[cur] & ~1ull;  // :1318
             ++hops;
             if (nvis + p.adj_stride > p.hash_limit) {  // visited set may fill up: hand over to the big-table pass
                 overflow = true;
@@ -379,7 +323,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 else if (it == 2) word = wreg[2];
                 else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
                 bool fresh = false;
-                if (j < deg) fresh = visited_test_and_set(hash, p.hash_log2, word);
+                if (j < deg && !(kBuild && word == self)) fresh = visited_test_and_set(hash, p.hash_log2, word);
                 const uint32_t m = __ballot_sync(0xffffffffu, fresh);
                 if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
                 n_w += __popc(m);
@@ -404,6 +348,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
             }
             if (tid == 0) atomicAdd(&p.counters[kCntFatal], 1u);
             size = 0;  // falls through to the "not enough results" fill
+        }
+        if (kBuild) {
+            if (tid == 0) p.exp_cnt[qi] = overflow ? 0u : min(hops, p.exp_cap);
+            __syncthreads();
+            continue;
         }
         // results (src/index_bipartite.cpp:2408-2419)
         if (size < p.k) {
@@ -450,16 +399,17 @@ static uint32_t auto_hash_log2(uint32_t L) {
     return lg;
 }
 
-static SearchKernel pick_kernel(bool ip, int gather, bool gh) {
+static SearchKernel pick_kernel(bool ip, int gather, bool gh, bool build) {
+    if (build) return ip ? rg_search_kernel<true, 2, true, true> : rg_search_kernel<false, 2, true, true>;
     if (gather == 2) {
-        if (gh) return ip ? rg_search_kernel<true, 2, true> : rg_search_kernel<false, 2, true>;
-        return ip ? rg_search_kernel<true, 2, false> : rg_search_kernel<false, 2, false>;
+        if (gh) return ip ? rg_search_kernel<true, 2, true, false> : rg_search_kernel<false, 2, true, false>;
+        return ip ? rg_search_kernel<true, 2, false, false> : rg_search_kernel<false, 2, false, false>;
     }
-    if (gh) return ip ? rg_search_kernel<true, 1, true> : rg_search_kernel<false, 1, true>;
-    return ip ? rg_search_kernel<true, 1, false> : rg_search_kernel<false, 1, false>;
+    if (gh) return ip ? rg_search_kernel<true, 1, true, false> : rg_search_kernel<false, 1, true, false>;
+    return ip ? rg_search_kernel<true, 1, false, false> : rg_search_kernel<false, 1, false, false>;
 }
 
-static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, Geometry *g) {
+static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g) {
     SearchParams &p = g->p;
     memset(&p, 0, sizeof(p));
     p.dim = ix->dim;
@@ -480,7 +430,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L);
     p.fallback = fallback ? 1u : 0u;
     // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
-    g->global_hash = fallback || hl > 15 || ix->cfg_hash_space != 1;
+    g->global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
     p.hash_log2 = hl;
     p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
@@ -508,7 +458,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     if (size_t(off) > size_t(ix->max_smem_optin))
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u needs %u bytes of shared memory per query (max %d)", L, off,
                         ix->max_smem_optin);
-    g->fn = pick_kernel(ix->metric != RG_METRIC_L2, g->gather, g->global_hash);
+    if (build) g->gather = 2;
+    g->fn = pick_kernel(ix->metric != RG_METRIC_L2, g->gather, g->global_hash, build);
     cudaError_t e = cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(g->smem_bytes));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, g->fn, g->warps * 32, g->smem_bytes);
     if (e != cudaSuccess) return rg::fail(RG_ERR_CUDA, "K1 launch configuration failed: %s", cudaGetErrorString(e));
@@ -528,19 +479,22 @@ static rg_status ensure(void **ptr, uint64_t *cap, uint64_t want, size_t elem) {
     return RG_OK;
 }
 
-static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t L,
-                               uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops,
-                               uint32_t *d_status, cudaStream_t st) {
-    if (!ix || !d_queries || !d_ids || !d_dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search: null argument");
+// d_exp_keys != nullptr selects the build-time variant: the queries are base rows node_lo .. node_lo + nq - 1
+static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t L,
+                                    uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops,
+                                    uint32_t *d_status, uint32_t node_lo, uint64_t *d_exp_keys, uint32_t *d_exp_cnt,
+                                    uint32_t exp_cap, cudaStream_t st) {
+    const bool build = d_exp_keys != nullptr;
+    if (!ix || (!build && (!d_queries || !d_ids || !d_dists))) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search: null argument");
     if (k == 0 || L == 0 || k > L) return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq must greater or equal than k (k=%u, L_pq=%u)", k, L);
     if (L > 8192) return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u too large (max 8192)", L);
     if (nq >= (1ull << 32)) return rg::fail(RG_ERR_INVALID_ARGUMENT, "too many queries in one batch");
     if (nq == 0) return RG_OK;
 
     Geometry g1, g2;
-    rg_status s = make_geometry(ix, k, L, false, &g1);
+    rg_status s = make_geometry(ix, k, L, false, build, &g1);
     if (s != RG_OK) return s;
-    s = make_geometry(ix, k, L, true, &g2);
+    s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
 
     // scratch: overflow list (one slot per query) and global hash slabs (one per CTA)
@@ -565,6 +519,10 @@ static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq
         g->p.overflow_list = ix->d_overflow_list;
         g->p.ghash = ix->d_ghash;
         g->p.nq = uint32_t(nq);
+        g->p.node_lo = node_lo;
+        g->p.exp_keys = d_exp_keys;
+        g->p.exp_cnt = d_exp_cnt;
+        g->p.exp_cap = exp_cap;
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
     g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
@@ -578,6 +536,19 @@ static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq
         RG_CUDA_OK(cudaMemcpyAsync(d_status + 1, ix->d_counters + kCntFatal, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
     return RG_OK;
+}
+
+static rg_status search_device(rg_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t L,
+                               uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops,
+                               uint32_t *d_status, cudaStream_t st) {
+    return search_device_impl(ix, d_queries, nq, k, L, d_ids, d_dists, d_cmps, d_hops, d_status, 0, nullptr, nullptr, 0, st);
+}
+
+// Build-time beam searches (connectivity enhancement): expanded nodes of base rows [node_lo, node_lo + count)
+rg_status search_expanded_device(rg_index *ix, uint32_t node_lo, uint64_t count, uint32_t L, uint64_t *d_exp_keys,
+                                 uint32_t *d_exp_cnt, uint32_t exp_cap, cudaStream_t st) {
+    return search_device_impl(ix, nullptr, count, 1, L, nullptr, nullptr, nullptr, nullptr, nullptr, node_lo, d_exp_keys,
+                              d_exp_cnt, exp_cap, st);
 }
 
 }  // namespace rg
