@@ -32,7 +32,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("RG_BENCH_N", 500_000)), help="base vectors")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("RG_BENCH_N", 10_000_000)), help="base vectors")
     ap.add_argument("--train", type=int, default=0, help="training queries for the build (0 = n/5, min 50K)")
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--dim", type=int, default=200)
@@ -56,30 +56,16 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------------
 # data + index preparation (not timed)
 # ---------------------------------------------------------------------------------------------------------
-def torch_exact_knn(base, queries, K, chunk=8192):
-    """Bootstrap exact kNN (inner product) for ground truth / the learn->base file until K2 (tcgen05) lands:
-    FP32 matmul (TF32 off) + top-k on the GPU.  Data preparation, never inside a timed region."""
+def gpu_exact_knn(base, queries, K):
+    """Exact inner-product kNN through the C ABI (K2-K4: tcgen05 GEMM + filter, FP32 re-rank, certificate)."""
     import torch
 
-    torch.backends.cuda.matmul.allow_tf32 = False
-    ids = torch.empty((queries.shape[0], K), dtype=torch.int64, device=base.device)
+    from mysteryann_b200 import capi
+
+    ids = torch.empty((queries.shape[0], K), dtype=torch.int32, device=base.device)
     dist = torch.empty((queries.shape[0], K), dtype=torch.float32, device=base.device)
-    bchunk = 1 << 20
-    for s in range(0, queries.shape[0], chunk):
-        q = queries[s:s + chunk]
-        best_v = best_i = None
-        for b0 in range(0, base.shape[0], bchunk):
-            sc = q @ base[b0:b0 + bchunk].T
-            v, i = sc.topk(min(K, sc.shape[1]), dim=1)
-            i += b0
-            if best_v is None:
-                best_v, best_i = v, i
-            else:
-                v2 = torch.cat([best_v, v], 1)
-                i2 = torch.cat([best_i, i], 1)
-                best_v, sel = v2.topk(K, dim=1)
-                best_i = i2.gather(1, sel)
-        ids[s:s + chunk], dist[s:s + chunk] = best_i, best_v
+    capi.knn_exact_device(base, queries, K, ids, dist, metric=capi.METRIC_IP, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     return ids, dist
 
 
@@ -91,41 +77,52 @@ def _sync(t):
 
 
 def prepare(args, rank, world, device):
-    """Returns dict(base (cuda), queries (cuda, this rank's batch), gt (numpy), offsets, adj, ep).  Rank 0 builds the
-    index once (host CPU BuildRoarGraph on all cores) and caches it in --cache; other ranks load it."""
+    """Returns dict(base (cuda), queries (cuda, this rank's batch), gt (numpy), index (capi.Index), info).
+    Rank 0 builds the index on its GPU (exact kNN of the training queries -> rg_build_roargraph_device) and caches the
+    index file in --cache; other ranks (and the --impl reference arm) load it."""
     import torch
     import torch.distributed as dist
 
-    from mysteryann_b200 import hostlib, io, synth
+    from mysteryann_b200 import capi, io, synth
 
     n_train = args.train or max(50_000, args.n // 5)
     base, train, test = synth.make_torch(args.n, n_train, args.queries * world, args.dim, seed=args.seed, device=device)
-    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}"
+    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}_gpu"
     os.makedirs(args.cache, exist_ok=True)
     index_path = os.path.join(args.cache, tag + ".index")
-    info = {"n_train": n_train, "index_cached": os.path.exists(index_path)}
+    info = {"n_train": n_train, "index_cached": os.path.exists(index_path), "builder": "rg_build_roargraph_device (GPU)"}
+    index = None
     if rank == 0 and not os.path.exists(index_path):
         t0 = time.time()
-        knn_ids, _ = torch_exact_knn(base, train, args.M_sq)
-        _sync(base)
+        knn_ids, _ = gpu_exact_knn(base, train, args.M_sq)
         info["knn_s"] = round(time.time() - t0, 2)
+        info["knn_tflops"] = round(2.0 * args.n * n_train * args.dim / (time.time() - t0) / 1e12, 1)
+        st = capi.knn_last_stats()
+        info["knn_exact_scans"] = st["exact_scans"]
         t0 = time.time()
-        hostlib.build()
-        hostlib.build_index(base.cpu().numpy(), train.cpu().numpy(), knn_ids.cpu().numpy().astype(np.uint32),
-                            index_path + ".tmp", metric=1, M_sq=args.M_sq, M_pjbp=args.M_pjbp, L_pjpq=args.L_pjpq,
-                            threads=os.cpu_count() or 1)
-        os.replace(index_path + ".tmp", index_path)
+        g = capi.Graph(base, knn_ids, M_sq=args.M_sq, M_pjbp=args.M_pjbp, L_pjpq=args.L_pjpq, metric=capi.METRIC_IP)
         info["graph_build_s"] = round(time.time() - t0, 2)
+        info["graph_build_phases_s"] = {k: round(v, 2) for k, v in g.phase_seconds.items()}
+        del knn_ids
+        ep, offsets, adj = g.download()
+        io.write_index(index_path + ".tmp", ep, offsets, adj)
+        os.replace(index_path + ".tmp", index_path)
+        index = capi.Index.from_graph(base, g, metric=capi.METRIC_IP)
+        info.update(avg_degree=round(g.nnz / args.n, 2), max_degree=int(g.max_degree), ep=int(ep))
+        g.close()
+        del offsets, adj
     if world > 1:
         dist.barrier()
     del train
-    ep, offsets, adj = io.read_index(index_path)
+    torch.cuda.empty_cache()
+    if index is None:
+        ep, offsets, adj = io.read_index(index_path)
+        index = capi.Index(base, offsets, adj, ep, metric=capi.METRIC_IP, device=device.index or 0)
+        info.update(avg_degree=round(len(adj) / args.n, 2), max_degree=int(np.diff(offsets).max()), ep=int(ep))
+        del offsets, adj
     q = test[rank * args.queries:(rank + 1) * args.queries].contiguous()
-    gt, _ = torch_exact_knn(base, q, args.k)
-    _sync(base)
-    info.update(avg_degree=round(len(adj) / args.n, 2), max_degree=int(np.diff(offsets).max()), ep=int(ep))
-    return dict(base=base, queries=q, gt=gt.cpu().numpy().astype(np.uint32), offsets=offsets, adj=adj, ep=ep,
-                info=info, index_path=index_path)
+    gt, _ = gpu_exact_knn(base, q, args.k)
+    return dict(base=base, queries=q, gt=gt.cpu().numpy().astype(np.uint32), index=index, info=info, index_path=index_path)
 
 
 def recall_at_k(ids, gt, k):
@@ -203,7 +200,7 @@ def run_ours(args):
         dist.barrier()
     d = prepare(args, rank, world, device)
     nq, k, dim = args.queries, args.k, args.dim
-    ix = capi.Index(d["base"], d["offsets"], d["adj"], d["ep"], metric=capi.METRIC_IP, device=local)
+    ix = d["index"]
     ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
@@ -238,6 +235,7 @@ def run_ours(args):
     search(L_sel)
     torch.cuda.synchronize()
     recall = recall_at_k(ids.cpu().numpy().view(np.uint32), d["gt"], k)
+    n_overflow = ix.last_overflow
     sum_cmps = float(cmps.sum().item())
     mean_hops = float(hops.float().mean().item())
     assert status.cpu().tolist() == [0, 0], "search reported short/overflowed queries"
@@ -312,9 +310,9 @@ def run_ours(args):
                                    f"RoarGraph M_sq={args.M_sq} M_pjbp={args.M_pjbp} L_pjpq={args.L_pjpq}",
                        "n_base": args.n, "dim": dim, "queries_per_gpu": nq, "k": k, "L_pq": L_sel,
                        "recall_at_10": round(recall, 4), "recall_sweep": sweep, "mean_cmps": round(sum_cmps / nq, 1),
-                       "mean_hops": round(mean_hops, 1), "parallelism": f"queries sharded over {world} GPU(s), index replicated",
+                       "mean_hops": round(mean_hops, 1), "visited_overflow_queries": n_overflow, "parallelism": f"queries sharded over {world} GPU(s), index replicated",
                        "l2": "256 MiB flush write between timed iterations", "index": d["info"],
-                       "knn_bootstrap": "torch fp32 matmul+topk (data prep, untimed)"},
+                       "ground_truth": "rg_knn_exact_device (exact, FP32 re-ranked)"},
             "e2e": {"value": round(nq * world / (e2e_ms / args.steps * 1e-3), 1), "unit": "queries/s",
                     "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 8 + 8,
                     "api": "rg_search_batch (C ABI, pinned host buffers)"},
@@ -325,41 +323,60 @@ def run_ours(args):
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            cb = cpu_baseline(args, d, L_sel)
-            cb.pop("_res")
-            out["cpu_baseline"] = cb
+            out["cpu_baseline"] = cpu_baseline(args, d, L_sel)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, d, L, threads=None, sample=None):
-    """The reference's CPU search (oracle/_ref when it is loadable, else the C port) on a bounded query sample."""
-    from mysteryann_b200 import io
-    from oracle.binding import Oracle, Ref, ref_available
+class CpuReference:
+    """The reference's CPU search (oracle/_ref when it is loadable, else the C port) on the host cores.  Opened once:
+    the base is written as an fbin next to the cached index and loaded by the reference's own loader."""
 
-    sample = min(sample or args.cpu_sample, args.queries)
-    q = d["queries"][:sample].cpu().numpy()
-    base = d["base"].cpu().numpy()
-    if ref_available():
-        r = Ref()
-        threads = threads or r.num_procs()
-        with tempfile.TemporaryDirectory() as tmp:
-            fb = os.path.join(tmp, "base.fbin")
-            io.write_fbin(fb, base)
-            h = r.open(fb, d["index_path"], metric=1, threads=threads)
-            res = r.search(h, q, args.k, L, threads=threads, warmup=True)
-            r.close(h)
-        kind = "reference"
-    else:
-        o = Oracle()
-        threads = threads or o.num_procs()
-        res = o.search(base, d["offsets"], d["adj"], d["ep"], q, args.k, L, metric=1, threads=threads)
-        kind = "port"
-    return {"value": round(sample / res["seconds"], 1), "unit": "queries/s", "cores": threads, "kind": kind,
-            "sample": f"first {sample} of the {args.queries} queries, L_pq={L}, OpenMP schedule(dynamic,1) like "
-                      "tests/test_search_roargraph.cpp:203", "_res": res}
+    def __init__(self, args, d):
+        from mysteryann_b200 import io
+        from oracle.binding import Oracle, Ref, ref_available
+
+        self.args, self.d = args, d
+        self.queries = d["queries"].cpu().numpy()
+        if ref_available():
+            self.kind, self.r = "reference", Ref()
+            self.threads = self.r.num_procs()
+            fb = os.path.join(args.cache, f"base_n{args.n}_d{args.dim}_s{args.seed}.fbin")
+            if not os.path.exists(fb):
+                io.write_fbin(fb + ".tmp", d["base"].cpu().numpy())
+                os.replace(fb + ".tmp", fb)
+            self.h = self.r.open(fb, d["index_path"], metric=1, threads=self.threads)
+        else:
+            self.kind, self.o = "port", Oracle()
+            self.threads = self.o.num_procs()
+            self.base = d["base"].cpu().numpy()
+            self.ep, self.offsets, self.adj = io.read_index(d["index_path"])
+
+    def search(self, L, sample):
+        q = self.queries[:sample]
+        if self.kind == "reference":
+            return self.r.search(self.h, q, self.args.k, L, threads=self.threads, warmup=True)
+        return self.o.search(self.base, self.offsets, self.adj, self.ep, q, self.args.k, L, metric=1, threads=self.threads)
+
+    def report(self, L, sample, res):
+        return {"value": round(sample / res["seconds"], 1), "unit": "queries/s", "cores": self.threads, "kind": self.kind,
+                "sample": f"first {sample} of the {self.args.queries} queries, L_pq={L}, OpenMP schedule(dynamic,1) like "
+                          "tests/test_search_roargraph.cpp:203"}
+
+    def close(self):
+        if self.kind == "reference":
+            self.r.close(self.h)
+
+
+def cpu_baseline(args, d, L):
+    ref = CpuReference(args, d)
+    sample = min(args.cpu_sample, args.queries)
+    res = ref.search(L, sample)
+    out = ref.report(L, sample, res)
+    ref.close()
+    return out
 
 
 def run_reference(args):
@@ -370,33 +387,39 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    assert torch.cuda.is_available(), "the index for the reference arm is prepared on the GPU (data prep, untimed)"
+    from mysteryann_b200 import build
+
+    build.build()
+    device = torch.device("cuda", 0)
     d = prepare(args, 0, 1, device)
+    ref = CpuReference(args, d)
     # same beam width rule as our arm: smallest L reaching the recall target (on the CPU sample)
     L_sel = args.L
     sample = min(args.cpu_sample, args.queries)
     if not L_sel:
         for L in L_SWEEP:
-            cb = cpu_baseline(args, d, L, sample=min(sample, 1000))
-            if recall_at_k(cb["_res"]["ids"], d["gt"][:len(cb["_res"]["ids"])], args.k) >= args.recall:
+            res = ref.search(L, min(sample, 1000))
+            if recall_at_k(res["ids"], d["gt"][:len(res["ids"])], args.k) >= args.recall:
                 L_sel = L
                 break
         L_sel = L_sel or L_SWEEP[-1]
     times = []
     for _ in range(args.warmup + args.steps):
-        cb = cpu_baseline(args, d, L_sel, sample=sample)
-        times.append(sample / cb["value"])
+        res = ref.search(L_sel, sample)
+        times.append(res["seconds"])
     t = float(np.mean(times[args.warmup:]))
     value = sample / t
-    cb.pop("_res")
+    cb = ref.report(L_sel, sample, res)
     cb["value"] = round(value, 1)
+    ref.close()
     out = {"impl": "reference", "metric": "QPS at recall@10=0.9 (IP, OOD queries)", "value": round(value, 1),
            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.n}x{args.dim} fp32 IP base, {args.queries} OOD queries, k={args.k}, "
                                   f"L_pq={L_sel}; each step = {sample}-query sample on {cb['cores']} host threads",
-                      "n_base": args.n, "dim": args.dim, "k": args.k, "L_pq": L_sel},
+                      "n_base": args.n, "dim": args.dim, "k": args.k, "L_pq": L_sel, "index": d["info"]},
            "cpu_baseline": cb,
            "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

@@ -86,6 +86,8 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
                                      int hash_log2);
 /* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA). */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
+/* Diagnostics (synchronises the device): queries of the last batch that were redone by the big-table visited-set pass. */
+RG_API uint32_t rg_search_last_overflow_count(rg_index *index);
 /* Number of kernel launches issued by this library on behalf of `index` so far. */
 RG_API uint64_t rg_index_launch_count(const rg_index *index);
 

@@ -20,7 +20,7 @@ RG_ERR_NO_DEVICE = 5
 METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
-           "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option",
+           "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
            "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
            "rg_index_create_from_graph"]
@@ -60,6 +60,8 @@ def lib():
     L.rg_search_configure.argtypes = [vp, i32, i32, i32, i32, i32]
     L.rg_search_set_option.restype = i32
     L.rg_search_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.rg_search_last_overflow_count.restype = u32
+    L.rg_search_last_overflow_count.argtypes = [vp]
     L.rg_index_launch_count.restype = u64
     L.rg_index_launch_count.argtypes = [vp]
     L.rg_knn_exact.restype = i32
@@ -142,6 +144,10 @@ class Index:
     def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0):
         _check(lib().rg_search_configure(self._h, gather, warps_per_query, ctas_per_sm, stage_rows, hash_log2))
         _check(lib().rg_search_set_option(self._h, b"hash_space", hash_space))
+
+    @property
+    def last_overflow(self) -> int:
+        return int(lib().rg_search_last_overflow_count(self._h))
 
     @property
     def launches(self) -> int:

@@ -390,10 +390,12 @@ struct Geometry {
 
 static uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-static uint32_t auto_hash_log2(uint32_t L) {
-    // expected worst-case visited nodes per query ~ 1000 + 30 L (max cmps 1371 @L=10 ...
-    // 13702 @L=500); outliers take the exact big-table fallback pass, so this only affects speed.
-    const double want = (1000.0 + 30.0 * L) / 0.8;
+static uint32_t auto_hash_log2(uint32_t L, bool global_space) {
+    // visited nodes per query ~ 1000 + 30 L on the 100K probe set (max cmps 1371 @L=10 ... 13702 @L=500)
+    // and ~1.7x that at 10M (mean 3180 @L=60).  A slab in global memory is sized for a load factor <= 0.4 at that
+    // estimate (short probe chains, overflow pass practically never needed); a shared-memory table for <= 0.8.
+    // Outliers take the exact big-table fallback pass, so this only affects speed.
+    const double want = (1000.0 + 30.0 * L) / (global_space ? 0.4 : 0.8);
     uint32_t lg = 10;
     while ((1u << lg) < want && lg < 22) ++lg;
     return lg;
@@ -427,7 +429,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
     const uint32_t W = uint32_t(g->warps);
 
-    uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L);
+    uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || ix->cfg_hash_space != 1);
     p.fallback = fallback ? 1u : 0u;
     // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
     g->global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
@@ -465,7 +467,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     if (e != cudaSuccess) return rg::fail(RG_ERR_CUDA, "K1 launch configuration failed: %s", cudaGetErrorString(e));
     if (g->ctas_per_sm < 1) return rg::fail(RG_ERR_INTERNAL, "K1 does not fit on an SM (L_pq=%u)", L);
     if (ix->cfg_ctas) g->ctas_per_sm = std::min(g->ctas_per_sm, ix->cfg_ctas);
-    if (fallback) g->ctas_per_sm = 1;  // few heavy queries, big global tables: keep the slab count small
+    if (fallback) g->ctas_per_sm = std::min(g->ctas_per_sm, 4);  // big global tables: keep the slab count small
     return RG_OK;
 }
 
@@ -501,7 +503,7 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     s = ensure((void **)&ix->d_overflow_list, &ix->overflow_cap, nq, sizeof(uint32_t));
     if (s != RG_OK) return s;
     const int grid1 = int(std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm));
-    const int grid2 = ix->sm_count;  // fallback pass: few, heavy queries; one CTA per SM
+    const int grid2 = ix->sm_count * g2.ctas_per_sm;  // fallback pass: few, heavy queries
     uint64_t need_hash = uint64_t(grid2) << g2.p.hash_log2;
     if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1) << g1.p.hash_log2);
     s = ensure((void **)&ix->d_ghash, &ix->ghash_words, need_hash, sizeof(uint32_t));
@@ -562,6 +564,16 @@ rg_status rg_search_batch_device(rg_index *ix, const float *d_queries, uint64_t 
     rg::DeviceGuard guard(ix->device);
     return rg::search_device(ix, d_queries, nq, k, L, d_ids, d_dists, d_cmps, d_hops, d_status,
                              static_cast<cudaStream_t>(cuda_stream));
+}
+
+// diagnostics: queries of the last batch whose visited set outgrew the primary table and were redone by the big-table pass
+uint32_t rg_search_last_overflow_count(rg_index *ix) {
+    if (!ix) return 0;
+    rg::DeviceGuard guard(ix->device);
+    uint32_t v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(&v, ix->d_counters + rg::kCntOverflow, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return v;
 }
 
 rg_status rg_search_batch(rg_index *ix, const float *queries, uint64_t nq, uint32_t k, uint32_t L, uint32_t *ids,
