@@ -106,6 +106,8 @@ def prepare(args, rank, world, device):
         del knn_ids
         ep, offsets, adj = g.download()
         io.write_index(index_path + ".tmp", ep, offsets, adj)
+        np.savez(index_path + ".csr.tmp.npz", ep=np.uint32(ep), offsets=offsets, adj=adj)  # fast reload for the other ranks
+        os.replace(index_path + ".csr.tmp.npz", index_path + ".csr.npz")
         os.replace(index_path + ".tmp", index_path)
         index = capi.Index.from_graph(base, g, metric=capi.METRIC_IP)
         info.update(avg_degree=round(g.nnz / args.n, 2), max_degree=int(g.max_degree), ep=int(ep))
@@ -116,7 +118,11 @@ def prepare(args, rank, world, device):
     del train
     torch.cuda.empty_cache()
     if index is None:
-        ep, offsets, adj = io.read_index(index_path)
+        if os.path.exists(index_path + ".csr.npz"):
+            z = np.load(index_path + ".csr.npz")
+            ep, offsets, adj = int(z["ep"]), z["offsets"], z["adj"]
+        else:
+            ep, offsets, adj = io.read_index(index_path)
         index = capi.Index(base, offsets, adj, ep, metric=capi.METRIC_IP, device=device.index or 0)
         info.update(avg_degree=round(len(adj) / args.n, 2), max_degree=int(np.diff(offsets).max()), ep=int(ep))
         del offsets, adj
