@@ -18,6 +18,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -28,63 +30,84 @@
 namespace rg {
 namespace knn {
 
-constexpr int kTileM = 128;      // queries per MMA (TMEM lanes); a CTA keeps 1 or 2 such halves resident
-constexpr int kTileN = 128;      // base rows per MMA tile (TMEM columns per accumulator)
+constexpr int kTileM = 128;      // queries per CTA (its 128 TMEM lanes); the CTA pair's MMA covers 2 x 128
+constexpr int kHalfN = 128;      // base rows each CTA of the pair stages per tile
+constexpr int kPairN = 256;      // base rows per MMA tile (TMEM columns per accumulator)
+constexpr int kTileN = kHalfN;   // TMA box rows
 constexpr int kSlabK = 64;       // FP16 elements per K slab = 128 bytes = one 128B-swizzle row
 constexpr int kSlabBytes = kTileN * kSlabK * 2;  // 16 KB
 constexpr int kUmmaK = 16;
 constexpr int kMaxSlabs = 8;     // dim <= 512
-constexpr int kEpiWarps = 8;     // epilogue warps: warp w reads TMEM lanes 32*(w%4).., column half w/4
-constexpr int kThreads = (kEpiWarps + 2) * 32;  // + warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
+constexpr int kEpiWarps = 16;    // epilogue warps: warp w reads TMEM lanes 32*(w%4).., column quarter w/4 (64 columns)
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // + warp 16 TMA producer, warp 17 MMA issuer + TMEM owner
 constexpr uint32_t kCap = 1024;  // candidate list capacity per query
-constexpr int kChunkTiles = 32;  // base tiles per work unit (A stays resident for a whole unit)
+constexpr uint32_t kStageSlots = 4;  // per-lane shared-memory slots for candidates found by the GEMM epilogue
+constexpr int kChunkTiles = 64;  // base tiles (256 rows) per work unit (the query tile stays resident for a whole unit)
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers (tcgen05 / TMA)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // relaxed: nothing written by this thread is read through the barrier (the TMEM loads have completed in
+    // tcgen05.wait::ld; tcgen05.fence::before_thread_sync orders them before the arrive); a release at cluster
+    // scope would cost a memory fence per tile and warp
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are
+// signalled on `bar_cluster_addr`, a barrier of the pair's leader CTA (cute SM100_TMA_2SM_LOAD_2D).
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
             smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)), "r"(cols)
+// TMEM of a CTA pair: the same warp of both CTAs allocates / frees (cute::TMEM::Allocator2Sm)
+__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)), "r"(cols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same, descriptors given as (low word, shared high word): low = smem address >> 4 (advance 2 per 32-byte K step)
-__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
-                                              uint32_t accumulate) {
+// One MMA of the CTA pair, issued by one thread of the leader: D[256 x N] (+)= A[256 x 16] * B[N x 16]^T, FP16 operands
+// from both CTAs' shared memory (same offsets), FP32 accumulators in both CTAs' TMEM.  Descriptors are given as
+// (low word, shared high word): low = smem address >> 4 (advance 2 per 32-byte K step).
+__device__ __forceinline__ void umma2_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
         "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {  // arrives on `bar` when all prior MMAs of this thread retire
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
-                 : "memory");
+// arrives (count 1) on the barrier at this offset in BOTH CTAs when all prior MMAs of this thread retire
+__device__ __forceinline__ void umma2_commit(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+        "h"(uint16_t(3))
+        : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 consecutive FP32 columns of the accumulator -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 32 lanes x 32 consecutive FP32 columns of the accumulator -> 32 registers per thread (asynchronous: tmem_ld_wait())
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -95,22 +118,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-// Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor): start>>4 | SBO(1024 B)>>4 <<32 |
-// version 1 <<46 | layout SWIZZLE_128B(2) <<61.  LBO is ignored for swizzled K-major operands.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
-}
-// Generic K-major swizzled descriptor: layout 2 = 128B (64 halves per row), 4 = 64B (32 halves), 6 = 32B (16 halves);
-// SBO = 8 rows x row bytes.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t layout, uint32_t sbo_bytes) {
-    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(layout) << 61);
-}
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major, swizzled: low word = start address >> 4,
+// high word = SBO (8 rows x row bytes) >> 4 | version 1 << 14 | layout << 29 (2 = 128B swizzle: 64 halves per row,
+// 4 = 64B: 32 halves, 6 = 32B: 16 halves).  LBO is ignored for swizzled K-major operands.
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=F32 (1<<4), A=B=F16 (0), K-major both,
-// N>>3 at bit 17, M>>4 at bit 24.
-constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(kTileN >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
+// N>>3 at bit 17, M>>4 at bit 24 (M = 256: the pair's two 128-row halves).
+constexpr uint32_t kIdesc2 = (1u << 4) | (uint32_t(kPairN >> 3) << 17) | (uint32_t((2 * kTileM) >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------------------
 // FP32 -> FP16 slab layout [nslab][rows_pad][64], scaled by a power of two; also squared norms / max |x|
@@ -150,18 +166,23 @@ __global__ void to_half_slabs_kernel(const float *__restrict__ x, uint64_t rows,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: GEMM + threshold filter
+// K2: GEMM + threshold filter.  CTA PAIR (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 queries (128 TMEM
+// lanes in each CTA) x 256 base rows (each CTA stages 128 of them), so every SM reads 4 KB of A + 4 KB of B from its
+// shared memory per 128 tensor cycles (64 B/clk) instead of 128 B/clk for a 128x128 single-CTA tile, and a B slab
+// fetched from L2 feeds 256 queries.  The query tile stays resident in shared memory for a whole work unit
+// (chunk_tiles base tiles) and is double buffered across units when the budget allows.
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmParams {
     uint32_t n_full;       // full 64-wide K slabs (128B swizzle)
     uint32_t tail_k;       // 0, 16 (32B swizzle) or 32 (64B swizzle): width of the last, narrower K slab
-    uint32_t mh;           // query halves of 128 rows resident per CTA (1 or 2): B traffic per FLOP ~ 1/mh
-    uint32_t a_half_bytes; // shared-memory bytes of one A half (all its slabs)
+    uint32_t a_bytes;      // shared-memory bytes of one resident query tile (128 rows, all its slabs), 1024-aligned
+    uint32_t a_bufs;       // 1 or 2 query-tile buffers
     uint32_t nq;           // valid queries in this batch
-    uint32_t m_tiles;      // ceil(nq / (128*mh))
+    uint32_t m_tiles;      // ceil(nq / 256)
+    uint32_t chunk_tiles;  // base tiles (of 256 rows) per work unit
     uint64_t q_rows_pad;   // padded row count of the query arrays
     uint64_t b_rows_pad;   // padded row count of the base arrays
-    uint64_t row_lo;       // first base row of this block (multiple of 128)
+    uint64_t row_lo;       // first base row of this block (multiple of 256)
     uint32_t n_tiles;      // base tiles in this block
     uint64_t n_valid;      // number of real base rows (ids >= n_valid are padding)
     uint64_t id_base;      // global id of base row 0
@@ -174,107 +195,188 @@ struct GemmParams {
     uint32_t n_stages;     // B slab ring depth
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+// filter value of accumulator column i: IP the raw accumulator, L2 the accumulator minus |b|^2 * scale/2
+template <bool kL2>
+__device__ __forceinline__ float filt(uint32_t raw, const float *bn, int i, float half_scale) {
+    return kL2 ? fmaf(-half_scale, bn[i], __uint_as_float(raw)) : __uint_as_float(raw);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // FMNMX3
+// 3-ary max tree over the 32 filter values of one accumulator slice (17 instructions); the inner nodes are kept so the
+// rare hit can be located by walking down the tree instead of testing all 32 columns
+struct MaxTree {
+    float a[11];  // a[i] = max of columns 3i..3i+2 (a[10]: columns 30, 31)
+    float b[4];   // b[g] = max of a[3g..3g+2] (b[3]: a[9], a[10])
+    float m;
+};
+template <bool kL2>
+__device__ __forceinline__ void build_tree(const uint32_t (&v)[32], const float *bn, float half_scale, MaxTree &t) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        t.a[i] = max3(filt<kL2>(v[3 * i], bn, 3 * i, half_scale), filt<kL2>(v[3 * i + 1], bn, 3 * i + 1, half_scale),
+                      filt<kL2>(v[3 * i + 2], bn, 3 * i + 2, half_scale));
+    t.a[10] = fmaxf(filt<kL2>(v[30], bn, 30, half_scale), filt<kL2>(v[31], bn, 31, half_scale));
+#pragma unroll
+    for (int g = 0; g < 3; ++g) t.b[g] = max3(t.a[3 * g], t.a[3 * g + 1], t.a[3 * g + 2]);
+    t.b[3] = fmaxf(t.a[9], t.a[10]);
+    t.m = fmaxf(max3(t.b[0], t.b[1], t.b[2]), t.b[3]);
+}
+// a lane whose staging slots are full appends directly (dense first blocks only)
+__device__ __noinline__ void direct_append(uint32_t *count, uint64_t *my_cand, uint64_t key) {
+    const uint32_t pos = atomicAdd(count, 1u);
+    if (pos < kCap) my_cand[pos] = key;
+}
+// Hit path of one lane: walk the max tree down to the columns that beat the threshold and STAGE them in the lane's
+// shared-memory slots st[j * 32] (j < kStageSlots).  Nothing here waits on global memory: a returning atomic per hit
+// (~700 cycles) in one of the pair's 16 epilogue warps would delay the accumulator hand-back of the whole pair.
+template <bool kL2>
+__device__ __forceinline__ uint32_t stage_hits(const MaxTree &t, const uint32_t (&v)[32], const float *bn, float half_scale,
+                                               float theta, float inv_scale, uint64_t row_first, uint64_t n_valid, uint64_t *st,
+                                               uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (t.b[g] > theta) {
+#pragma unroll
+            for (int tt = 3 * g; tt < 3 * g + 3 && tt < 11; ++tt) {
+                if (t.a[tt] > theta) {
+#pragma unroll
+                    for (int i = 3 * tt; i < 3 * tt + 3 && i < 32; ++i) {
+                        if (filt<kL2>(v[i], bn, i, half_scale) > theta) {
+                            const uint64_t row = row_first + i;
+                            const float a = __uint_as_float(v[i]);
+                            const float sc = kL2 ? fmaf(-2.f * inv_scale, a, bn[i]) : -(a * inv_scale);
+                            if (row < n_valid) {
+                                const uint64_t key = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
+                                if (n_st < kStageSlots) {
+                                    st[n_st * 32] = key;
+                                    ++n_st;
+                                } else {
+                                    direct_append(count, my_cand, key);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return n_st;
+}
+// one reservation per lane for everything it staged, then the copies
+__device__ __noinline__ void stage_flush(const uint64_t *st, uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
+    if (n_st) {
+        const uint32_t base = atomicAdd(count, n_st);
+        for (uint32_t j = 0; j < n_st; ++j)
+            if (base + j < kCap) my_cand[base + j] = st[j * 32];
+    }
+}
+
+template <bool kL2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                        const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bt,
                        const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // [A: mh halves x a_half_bytes][B ring: n_stages x 16 KB][barriers][tmem slot][bnorm 2 x 128 floats]
+    // [A: a_bufs x a_bytes][B ring: n_stages x 16 KB][barriers][tmem slot][bnorm 2 x 256 floats]; identical in both CTAs
     unsigned char *smem_a = smem;
-    unsigned char *smem_b = smem + size_t(p.mh) * p.a_half_bytes;
+    unsigned char *smem_b = smem + size_t(p.a_bufs) * p.a_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + size_t(p.n_stages) * kSlabBytes);
-    uint64_t *full = bars;                      // [n_stages]
-    uint64_t *empty = bars + 16;                // [n_stages]
-    uint64_t *a_full = bars + 32;
-    uint64_t *a_empty = bars + 33;
-    uint64_t *tmem_full = bars + 34;            // [2]
-    uint64_t *tmem_empty = bars + 36;           // [2]
+    uint64_t *full = bars;                      // [n_stages]  used in the leader CTA only (both CTAs' TMA signal it)
+    uint64_t *empty = bars + 16;                // [n_stages]  one per CTA, released by the leader's multicast commit
+    uint64_t *a_full = bars + 32;               // [2]         leader only
+    uint64_t *a_empty = bars + 34;              // [2]         per CTA
+    uint64_t *tmem_full = bars + 36;            // [2]         per CTA (multicast commit)
+    uint64_t *tmem_empty = bars + 38;           // [2]         leader only: 2 x kEpiWarps arrivals (both CTAs' epilogues)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
-    float *s_bn = reinterpret_cast<float *>(bars + 48);  // [2][128]
+    float *s_bn = reinterpret_cast<float *>(bars + 48);  // [2][256]
+    uint64_t *s_stage = reinterpret_cast<uint64_t *>(s_bn + 2 * kPairN);  // [kEpiWarps][kStageSlots][32]
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t nslab = p.n_full + (p.tail_k ? 1u : 0u);
-    const uint32_t tail_bytes = kTileN * p.tail_k * 2;
-    const uint32_t tmem_cols = p.mh * 2 * kTileN;  // 256 or 512
+    const uint32_t rank = cluster_ctarank();    // 0 = leader (issues every MMA), 1 = peer
+    const uint32_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const uint32_t tail_bytes = kHalfN * p.tail_k * 2;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
         for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_full[a], 1);
+            mbar_init(&a_empty[a], 1);
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], kEpiWarps);
+            mbar_init(&tmem_empty[a], 2 * kEpiWarps);
         }
         fence_mbar_init();
     }
-    if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == kEpiWarps + 1) tmem_alloc2(tmem_slot, 512);   // the same warp of both CTAs allocates the pair's columns
     tc_fence_before();
-    __syncthreads();
+    cluster_sync();                                            // barriers of both CTAs initialised before any remote use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t chunks = (p.n_tiles + kChunkTiles - 1) / kChunkTiles;
-    const uint32_t units = chunks * p.m_tiles;  // chunk-major: concurrently running CTAs share the B chunk in L2
-    const uint32_t rows_per_cta = kTileM * p.mh;
+    const uint32_t chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
+    const uint32_t units = chunks * p.m_tiles;  // chunk-major: concurrently running pairs share the B chunk in L2
 
     if (warp == kEpiWarps) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs; each loads its 128 query rows and its 128 base rows) ======
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0;
-            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            uint32_t stage = 0, phase = 0, abuf = 0, a_ph = 0;  // a_ph: bit b = phase of a_empty[b]
+            const uint32_t full_leader = mapa_u32(smem_u32(full), 0);
+            const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
+            const uint32_t a_tx = p.n_full * kSlabBytes + tail_bytes;
+            for (uint32_t u = cid; u < units; u += ncl) {
                 const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
-                mbar_wait(a_empty, a_phase ^ 1);  // MMAs of the previous unit no longer read A
-                a_phase ^= 1;
-                mbar_arrive_expect_tx(a_full, p.mh * (p.n_full * kSlabBytes + tail_bytes));
-                for (uint32_t h = 0; h < p.mh; ++h) {
-                    unsigned char *ah = smem_a + size_t(h) * p.a_half_bytes;
-                    const uint64_t qrow = uint64_t(m) * rows_per_cta + h * kTileM;
-                    for (uint32_t j = 0; j < p.n_full; ++j)
-                        tma_load_2d(ah + size_t(j) * kSlabBytes, &map_q, 0, int(j * p.q_rows_pad + qrow), a_full);
-                    if (p.tail_k) tma_load_2d(ah + size_t(p.n_full) * kSlabBytes, &map_qt, 0, int(qrow), a_full);
-                }
-                const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+                mbar_wait(&a_empty[abuf], ((a_ph >> abuf) & 1u) ^ 1u);  // MMAs that read this buffer have retired
+                a_ph ^= 1u << abuf;
+                if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * a_tx);
+                unsigned char *ah = smem_a + size_t(abuf) * p.a_bytes;
+                const uint64_t qrow = uint64_t(m) * (2 * kTileM) + rank * kTileM;
+                for (uint32_t j = 0; j < p.n_full; ++j)
+                    tma_load_2d_pair(ah + size_t(j) * kSlabBytes, &map_q, 0, int(j * p.q_rows_pad + qrow), a_full_leader + abuf * 8);
+                if (p.tail_k) tma_load_2d_pair(ah + size_t(p.n_full) * kSlabBytes, &map_qt, 0, int(qrow), a_full_leader + abuf * 8);
+                const uint32_t t0 = c * p.chunk_tiles, t1 = min(p.n_tiles, t0 + p.chunk_tiles);
                 for (uint32_t t = t0; t < t1; ++t) {
-                    const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
-                    for (uint32_t j = 0; j < nslab; ++j) {
+                    const uint64_t row0 = p.row_lo + uint64_t(t) * kPairN + rank * kHalfN;
+                    for (uint32_t j = 0; j < p.n_full; ++j) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        if (j < p.n_full) {
-                            mbar_arrive_expect_tx(&full[stage], kSlabBytes);
-                            tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_b, 0, int(j * p.b_rows_pad + row0), &full[stage]);
-                        } else {
-                            mbar_arrive_expect_tx(&full[stage], tail_bytes);
-                            tma_load_2d(smem_b + size_t(stage) * kSlabBytes, &map_bt, 0, int(row0), &full[stage]);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * kSlabBytes);
+                        tma_load_2d_pair(smem_b + size_t(stage) * kSlabBytes, &map_b, 0, int(j * p.b_rows_pad + row0),
+                                         full_leader + stage * 8);
+                        if (++stage == p.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
                         }
+                    }
+                    if (p.tail_k) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * tail_bytes);
+                        tma_load_2d_pair(smem_b + size_t(stage) * kSlabBytes, &map_bt, 0, int(row0), full_leader + stage * 8);
                         if (++stage == p.n_stages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
                 }
+                if (++abuf == p.a_bufs) abuf = 0;
             }
         }
     } else if (warp == kEpiWarps + 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            uint32_t stage = 0, phase = 0, abuf = 0, a_ph = 0, acc = 0, acc_phase = 0;
             // descriptor words: low = (smem address >> 4) & 0x3FFF, high = SBO>>4 | version 1 <<14 | layout <<29
             const uint32_t hi_full = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t hi_tail = ((8u * p.tail_k * 2u) >> 4) | (1u << 14) | ((p.tail_k == 32 ? 4u : 6u) << 29);
-            const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
-            const uint32_t a_half16 = p.a_half_bytes >> 4;
             const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
-            const bool two = p.mh == 2;
-            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            for (uint32_t u = cid; u < units; u += ncl) {
                 const uint32_t c = u / p.m_tiles;
-                mbar_wait(a_full, a_phase);
-                a_phase ^= 1;
-                const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+                mbar_wait(&a_full[abuf], (a_ph >> abuf) & 1u);
+                a_ph ^= 1u << abuf;
+                const uint32_t a_lo0 = (smem_u32(smem_a + size_t(abuf) * p.a_bytes) & 0x3FFFFu) >> 4;
+                const uint32_t t0 = c * p.chunk_tiles, t1 = min(p.n_tiles, t0 + p.chunk_tiles);
                 for (uint32_t t = t0; t < t1; ++t) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator set
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // both epilogues drained this accumulator
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * (p.mh * kTileN);
+                    const uint32_t tmem_d = tmem_base + acc * kPairN;
                     for (uint32_t j = 0; j < p.n_full; ++j) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
@@ -282,14 +384,8 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         const uint32_t a_lo = a_lo0 + j * (kSlabBytes >> 4);
 #pragma unroll
                         for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k)
-                            umma_f16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, hi_full, kIdesc, (j | k) != 0 ? 1u : 0u);
-                        if (two) {
-#pragma unroll
-                            for (uint32_t k = 0; k < kSlabK / kUmmaK; ++k)
-                                umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16 + 2 * k, b_lo + 2 * k, hi_full, kIdesc,
-                                              (j | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(&empty[stage]);  // slab may be overwritten once these MMAs retire
+                            umma2_f16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, hi_full, kIdesc2, (j | k) != 0 ? 1u : 0u);
+                        umma2_commit(&empty[stage]);  // both CTAs' slab halves may be overwritten once these MMAs retire
                         if (++stage == p.n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -301,39 +397,38 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         const uint32_t b_lo = b_lo0 + stage * (kSlabBytes >> 4);
                         const uint32_t a_lo = a_lo0 + p.n_full * (kSlabBytes >> 4);
                         const uint32_t first = p.n_full ? 1u : 0u;
-                        umma_f16_lohi(tmem_d, a_lo, b_lo, hi_tail, kIdesc, first);
-                        if (p.tail_k == 32) umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, hi_tail, kIdesc, 1u);
-                        if (two) {
-                            umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16, b_lo, hi_tail, kIdesc, first);
-                            if (p.tail_k == 32) umma_f16_lohi(tmem_d + kTileN, a_lo + a_half16 + 2, b_lo + 2, hi_tail, kIdesc, 1u);
-                        }
-                        umma_commit(&empty[stage]);
+                        umma2_f16_lohi(tmem_d, a_lo, b_lo, hi_tail, kIdesc2, first);
+                        if (p.tail_k == 32) umma2_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, hi_tail, kIdesc2, 1u);
+                        umma2_commit(&empty[stage]);
                         if (++stage == p.n_stages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    umma_commit(&tmem_full[acc]);
+                    umma2_commit(&tmem_full[acc]);
                     if (++acc == 2) {
                         acc = 0;
                         acc_phase ^= 1;
                     }
                 }
-                umma_commit(a_empty);
+                umma2_commit(&a_empty[abuf]);
+                if (++abuf == p.a_bufs) abuf = 0;
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> threshold filter =====================
-        // mh == 2: warp w owns query half w/4 (all 128 columns); mh == 1: warps w and w+4 split the columns.
+        // warp w reads TMEM lanes 32*(w%4).. (its 32 queries) and the column quarter w/4 (64 base rows) of each tile:
+        // 4 warps per scheduler keep the TMEM loads and the max trees of different warps overlapped
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t quarter = warp & 3, part = warp >> 2;
-        const uint32_t h = (p.mh == 2) ? part : 0u;
-        const uint32_t col_lo = (p.mh == 2) ? 0u : part * (kTileN / 2);
-        const uint32_t col_hi = (p.mh == 2) ? uint32_t(kTileN) : (part + 1) * (kTileN / 2);
-        const uint32_t row_in_cta = h * kTileM + quarter * 32 + lane;  // TMEM lane (+ half) == query row of the CTA tile
-        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t c0 = part * 64;
+        const uint32_t row_in_pair = rank * kTileM + quarter * 32 + lane;
+        const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty), 0);
+        uint64_t *st = s_stage + size_t(warp) * (kStageSlots * 32) + lane;
+        uint32_t n_st = 0;  // candidates staged by this lane
+        for (uint32_t u = cid; u < units; u += ncl) {
             const uint32_t c = u / p.m_tiles, m = u % p.m_tiles;
-            const uint32_t q = m * rows_per_cta + row_in_cta;
+            const uint32_t q = m * (2 * kTileM) + row_in_pair;
             const bool q_valid = q < p.nq;
             const float tau = q_valid ? p.thr[q] : -INFINITY;
             const float scale = 1.f / p.inv_scale;            // power of two
@@ -341,72 +436,62 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const float half_scale = 0.5f * scale;            // L2
             const float theta_l2 = -tau * half_scale;
             uint64_t *my_cand = p.cand + uint64_t(q_valid ? q : 0) * kCap;
-            const uint32_t t0 = c * kChunkTiles, t1 = min(p.n_tiles, t0 + kChunkTiles);
+            const uint32_t t0 = c * p.chunk_tiles, t1 = min(p.n_tiles, t0 + p.chunk_tiles);
             for (uint32_t t = t0; t < t1; ++t) {
-                const uint64_t row0 = p.row_lo + uint64_t(t) * kTileN;
-                if (p.l2) {
-                    if (part == 0) {
-                        const uint64_t r = row0 + quarter * 32 + lane;
-                        s_bn[acc * kTileN + quarter * 32 + lane] = (r < p.n_valid) ? p.bnorm[r] : INFINITY;
+                const uint64_t row0 = p.row_lo + uint64_t(t) * kPairN;
+                if (kL2) {
+                    if (threadIdx.x < kPairN) {               // thread <-> column
+                        const uint64_t r = row0 + threadIdx.x;
+                        s_bn[acc * kPairN + threadIdx.x] = (r < p.n_valid) ? p.bnorm[r] : INFINITY;
                     }
-                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiWarps * 32) : "memory");
                 }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (p.mh * kTileN) + h * kTileN;
-#pragma unroll 1
-                for (uint32_t c0 = col_lo; c0 < col_hi; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    // "does any of my 32 accumulators beat the threshold": a max tree (no serial predicate chain) and one
-                    // compare on the raw, scaled value; v[] is only indexed with constants so it stays in registers.
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN + c0;
+                const float *bn = s_bn + acc * kPairN + c0;
+                {
+                    // two 32-column accumulator slices in flight, one wait
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32_nowait(taddr, v0);
+                    tmem_ld32_nowait(taddr + 32, v1);
+                    tmem_ld_wait();
+                    // "does any of my accumulators beat the threshold": a 3-input max tree (FMNMX3) over the raw, scaled
+                    // values and ONE compare; the slices are only indexed with constants so they stay in registers.
                     //   IP: -<q,b> < tau            <=>  acc > -tau * scale
                     //   L2: |b|^2 - 2<q,b> < tau    <=>  acc - |b|^2 * scale/2 > -tau * scale/2
-                    float d[32];
-                    if (p.l2) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) d[i] = fmaf(-half_scale, s_bn[acc * kTileN + c0 + i], __uint_as_float(v[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
-                    }
-                    float mx[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) mx[i] = fmaxf(d[i], d[i + 16]);
-#pragma unroll
-                    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; ++i) mx[i] = fmaxf(mx[i], mx[i + w]);
-                    const float theta = p.l2 ? theta_l2 : theta_raw;
-                    const bool any = mx[0] > theta;
-                    if (any) {  // rare: a few candidates per query per block
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float a = __uint_as_float(v[i]);
-                            if (d[i] > theta) {
-                                const uint64_t row = row0 + c0 + i;
-                                const float sc = p.l2 ? fmaf(-2.f * p.inv_scale, a, s_bn[acc * kTileN + c0 + i]) : -(a * p.inv_scale);
-                                if (row < p.n_valid) {
-                                    const uint32_t pos = atomicAdd(&p.cand_count[q], 1u);
-                                    if (pos < kCap) my_cand[pos] = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
-                                }
-                            }
-                        }
-                    }
+                    const float theta = kL2 ? theta_l2 : theta_raw;
+                    MaxTree t;
+                    build_tree<kL2>(v0, bn, half_scale, t);
+                    if (t.m > theta)  // rare per lane: a few candidates per query per block
+                        n_st = stage_hits<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st, n_st,
+                                               p.cand_count + q, my_cand);
+                    build_tree<kL2>(v1, bn + 32, half_scale, t);
+                    if (t.m > theta)
+                        n_st = stage_hits<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32, p.n_valid, st, n_st,
+                                               p.cand_count + q, my_cand);
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
+                if (n_st > kStageSlots / 2) {  // after the accumulator went back: keep room for the next tile's hits
+                    stage_flush(st, n_st, p.cand_count + q, my_cand);
+                    n_st = 0;
+                }
+            }
+            if (__any_sync(0xffffffffu, n_st > 0)) {  // the lane's query changes with the unit
+                stage_flush(st, n_st, p.cand_count + q, my_cand);
+                n_st = 0;
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
+    cluster_sync();   // the peer's shared memory and TMEM stay alive until the leader's last MMA has been consumed
+    if (warp == kEpiWarps + 1) tmem_dealloc2(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -768,8 +853,8 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     }
     const uint32_t nslab = n_full + (tail_k ? 1 : 0);
     const uint32_t tail_bytes = kTileN * tail_k * 2;
-    const uint32_t a_half_bytes = (n_full * kSlabBytes + tail_bytes + 1023) / 1024 * 1024;
-    const uint64_t b_rows_pad = (n + kTileN - 1) / kTileN * kTileN;
+    const uint32_t a_bytes = (n_full * kSlabBytes + tail_bytes + 1023) / 1024 * 1024;
+    const uint64_t b_rows_pad = (n + kPairN - 1) / kPairN * kPairN;
     const uint32_t kprime = std::min<uint32_t>(256, std::max<uint32_t>(K + K / 2, K + 32));
     const uint64_t q_batch = 32768;
     const uint64_t q_rows_pad = (std::min(nq, q_batch) + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
@@ -778,6 +863,15 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     RG_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
+    const bool trace = std::getenv("RG_KNN_TRACE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rg_knn] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     Scratch sc;
     __half *b16 = nullptr, *q16 = nullptr, *b16t = nullptr, *q16t = nullptr;
     float *bnorm = nullptr, *thr = nullptr;
@@ -796,6 +890,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(sc.alloc(&flag_list, q_batch));
     RG_CUDA_OK(sc.alloc(&cand, q_batch * kCap));
 
+    lap("scratch allocation");
     // scal[0] = max|b| bits, scal[1] = max |b|^2 bits, scal[2] = max|q| bits, scal[3] = #flagged
     RG_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
     absmax_kernel<<<sms * 8, 256, 0, st>>>(d_base, n * dim, scal + 0);
@@ -816,6 +911,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     // covers FP32 accumulation; L2 scores carry the factor 2 of -2<q,b>.
     const float eps_factor = 1.02f * std::ldexp(1.f, -10) * std::sqrt(max_bnorm2) * (ip ? 1.f : 2.f);
 
+    lap("base conversion");
     CUtensorMap map_q, map_b, map_qt, map_bt;
     rg_status s = RG_OK;
     if (n_full) {
@@ -829,19 +925,54 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         map_q = map_qt;
     }
 
-    // B ring depth from the shared-memory budget
-    // two resident query halves (M = 256 per B slab: half the L2->SM operand traffic per FLOP) when the ring still
-    // gets >= 4 stages, else one
-    const size_t misc = 48 * 8 + 2 * kTileN * sizeof(float) + 1024;
-    uint32_t mh = 2;
-    if (size_t(smem_max) < 2 * size_t(a_half_bytes) + 4 * size_t(kSlabBytes) + misc) mh = 1;
-    if (size_t(smem_max) < size_t(mh) * a_half_bytes + 2 * size_t(kSlabBytes) + misc)
+    // shared-memory budget: the resident query tile is double buffered across work units when the B ring still
+    // gets >= 4 stages; the ring takes the rest
+    const size_t misc = 48 * 8 + 2 * kPairN * sizeof(float) + size_t(kEpiWarps) * kStageSlots * 32 * 8 + 1024;
+    uint32_t a_bufs = 2;
+    if (size_t(smem_max) < 2 * size_t(a_bytes) + 4 * size_t(kSlabBytes) + misc) a_bufs = 1;
+    if (size_t(smem_max) < size_t(a_bufs) * a_bytes + 2 * size_t(kSlabBytes) + misc)
         return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim %u leaves no room for the operand ring", dim);
-    uint32_t n_stages = uint32_t((size_t(smem_max) - misc - size_t(mh) * a_half_bytes) / kSlabBytes);
+    uint32_t n_stages = uint32_t((size_t(smem_max) - misc - size_t(a_bufs) * a_bytes) / kSlabBytes);
     n_stages = std::min<uint32_t>(n_stages, 16);
-    const size_t gemm_smem = size_t(mh) * a_half_bytes + size_t(n_stages) * kSlabBytes + misc;
+    const size_t gemm_smem = size_t(a_bufs) * a_bytes + size_t(n_stages) * kSlabBytes + misc;
     (void)nslab;
-    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    // persistent grid: as many CTA pairs as the device can co-schedule (one CTA per SM, pairs on one TPC); the
+    // occupancy query costs tens of milliseconds, so its answer is cached per (device, shared-memory size)
+    uint32_t max_pairs = uint32_t(sms) / 2;
+    {
+        static std::mutex mu;
+        static std::vector<std::pair<uint64_t, uint32_t>> cache;
+        const uint64_t key = (uint64_t(dev) << 32) | uint64_t(gemm_smem);
+        std::lock_guard<std::mutex> lock(mu);
+        bool hit = false;
+        for (auto &e : cache)
+            if (e.first == key) {
+                max_pairs = e.second;
+                hit = true;
+            }
+        if (!hit) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(unsigned(sms) / 2 * 2);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = gemm_smem;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            int active = 0;
+            if (cudaOccupancyMaxActiveClusters(&active, knn_gemm_filter_kernel<false>, &cfg) == cudaSuccess && active > 0)
+                max_pairs = std::min<uint32_t>(max_pairs, uint32_t(active));
+            else
+                (void)cudaGetLastError();
+            cache.emplace_back(key, max_pairs);
+        }
+    }
     RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
@@ -849,6 +980,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
 
+    lap("tensor maps + attributes");
     uint64_t launches = 5, flagged_total = 0;
     for (uint64_t q0 = 0; q0 < nq; q0 += q_batch) {
         const uint32_t bq = uint32_t(std::min<uint64_t>(q_batch, nq - q0));
@@ -862,10 +994,11 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         memset(&gp, 0, sizeof(gp));
         gp.n_full = n_full;
         gp.tail_k = tail_k;
-        gp.mh = mh;
-        gp.a_half_bytes = a_half_bytes;
+        gp.a_bytes = a_bytes;
+        gp.a_bufs = a_bufs;
         gp.nq = bq;
-        gp.m_tiles = (bq + kTileM * mh - 1) / (kTileM * mh);
+        gp.m_tiles = (bq + 2 * kTileM - 1) / (2 * kTileM);
+        gp.chunk_tiles = kChunkTiles;
         gp.q_rows_pad = q_rows_pad;
         gp.b_rows_pad = b_rows_pad;
         gp.n_valid = n;
@@ -883,14 +1016,17 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         while (lo < b_rows_pad) {
             const uint64_t hi = std::min(b_rows_pad, lo + len);
             gp.row_lo = lo;
-            gp.n_tiles = uint32_t((hi - lo) / kTileN);
+            gp.n_tiles = uint32_t((hi - lo) / kPairN);
             const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
-            knn_gemm_filter_kernel<<<std::min<uint32_t>(units, sms), kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+            const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
+            if (ip) knn_gemm_filter_kernel<false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+            else knn_gemm_filter_kernel<true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
             knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(cand, cand_count, thr, overflow, bq, kprime);
             launches += 2;
             lo = hi;
             len = std::max<uint64_t>(len, lo);  // next block as large as everything seen so far
         }
+        lap("  batch: gemm + select");
         if (ip)
             knn_rerank_kernel<true><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
                                                                        eps_factor, max_bnorm2, bq, K, kprime, n, d_ids + q0 * K,
@@ -917,6 +1053,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             launches += 1;
         }
         RG_CUDA_OK(cudaGetLastError());
+        lap("  batch: rerank + exact scan");
     }
     RG_CUDA_OK(cudaStreamSynchronize(st));
     if (stats) {

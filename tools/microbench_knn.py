@@ -24,20 +24,22 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     capi.knn_exact_device(base, train, a.K, ids, d, stream=st)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    per_rep = []
     for _ in range(a.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         capi.knn_exact_device(base, train, a.K, ids, d, stream=st)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.reps
+        e1.record()
+        torch.cuda.synchronize()
+        per_rep.append(round(e0.elapsed_time(e1), 2))
+    ms = sum(per_rep) / a.reps
     flops = 2.0 * a.n * a.nq * a.dim
     peaks = json.load(open("MEASURED_PEAKS.json")) if __import__("os").path.exists("MEASURED_PEAKS.json") else {}
     tf = flops / (ms * 1e-3) / 1e12
     print(json.dumps(dict(n=a.n, nq=a.nq, dim=a.dim, K=a.K, ms=round(ms, 2), tflops_algorithmic=round(tf, 1),
                           frac_of_bf16_burst=round(tf / peaks.get("bf16_tflops", 1640.9), 4),
                           frac_of_bf16_sustained=round(tf / peaks.get("bf16_tflops_sustained", 1378.6), 4),
-                          stats=capi.knn_last_stats())))
+                          per_rep_ms=per_rep, stats=capi.knn_last_stats())))
 
 
 if __name__ == "__main__":
