@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--stage-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per query (0 = library default)")
     ap.add_argument("--hash-space", type=int, default=0)
+    ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
+    ap.add_argument("--adj-prefetch", type=int, default=None, help="K1 adjacency prefetch bit mask (None = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -92,11 +94,37 @@ def prepare(args, rank, world, device):
     index_path = os.path.join(args.cache, tag + ".index")
     info = {"n_train": n_train, "index_cached": os.path.exists(index_path), "builder": "rg_build_roargraph_device (GPU)"}
     index = None
-    if rank == 0 and not os.path.exists(index_path):
+    need_build = not os.path.exists(index_path)
+    if world > 1:  # every rank must agree (the file may appear while a slow rank is still generating data)
+        t = torch.tensor([int(need_build)], device=device)
+        dist.broadcast(t, src=0)
+        need_build = bool(t.item())
+    knn_ids = None
+    if need_build and world > 1:
+        # build kNN, base-sharded over the ranks: K2/K3 per shard, NCCL all-to-all of the per-shard lists, K4 merge,
+        # all-gather of the merged slices (mysteryann_b200/sharded_knn.py); rank 0 keeps the ids for the graph build
+        from mysteryann_b200 import sharded_knn
+
+        b = sharded_knn.shard_bounds(args.n, world)
+        torch.cuda.synchronize()
+        dist.barrier()
         t0 = time.time()
-        knn_ids, _ = gpu_exact_knn(base, train, args.M_sq)
+        knn_ids, _, _ = sharded_knn.knn_sharded(base[b[rank]:b[rank + 1]], b[rank], train, args.M_sq, metric=capi.METRIC_IP,
+                                                stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        dist.barrier()
         info["knn_s"] = round(time.time() - t0, 2)
         info["knn_tflops"] = round(2.0 * args.n * n_train * args.dim / (time.time() - t0) / 1e12, 1)
+        info["knn_parallelism"] = f"base sharded over {world} GPUs, NCCL all-to-all + K4 merge"
+        if rank != 0:
+            knn_ids = None
+    if rank == 0 and need_build:
+        if knn_ids is None:
+            t0 = time.time()
+            knn_ids, _ = gpu_exact_knn(base, train, args.M_sq)
+            info["knn_s"] = round(time.time() - t0, 2)
+            info["knn_tflops"] = round(2.0 * args.n * n_train * args.dim / (time.time() - t0) / 1e12, 1)
+            info["knn_parallelism"] = "1 GPU"
         st = capi.knn_last_stats()
         info["knn_exact_scans"] = st["exact_scans"]
         t0 = time.time()
@@ -113,6 +141,11 @@ def prepare(args, rank, world, device):
         info.update(avg_degree=round(g.nnz / args.n, 2), max_degree=int(g.max_degree), ep=int(ep))
         g.close()
         del offsets, adj
+        json.dump(info, open(index_path + ".info.json", "w"))  # build timings travel with the cached index
+    elif rank == 0 and os.path.exists(index_path + ".info.json"):
+        cached = json.load(open(index_path + ".info.json"))
+        cached.update(index_cached=True)
+        info = cached
     if world > 1:
         dist.barrier()
     del train
@@ -186,6 +219,19 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
+def load_traffic(args, L):
+    """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this same workload (profiles/k1_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one rg_search_kernel launch); None when the workload differs."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        w = t["workload"]
+        if (w["n_base"], w["dim"], w["queries"], w["L_pq"], w["k"]) == (args.n, args.dim, args.queries, L, args.k):
+            return int(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -207,7 +253,8 @@ def run_ours(args):
     d = prepare(args, rank, world, device)
     nq, k, dim = args.queries, args.k, args.dim
     ix = d["index"]
-    ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space)
+    ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space,
+                 l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
     dists = torch.empty((nq, k), dtype=torch.float32, device=device)
@@ -324,7 +371,7 @@ def run_ours(args):
                     "api": "rg_search_batch (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 4), "traffic": load_traffic(args, L_sel), "peak_kind": peak_kind,
                          "kernel": "rg_search_kernel", "algorithmic_bytes_per_launch": int(alg_bytes)},
             "clocks": sampler.summary(),
         }

@@ -84,7 +84,10 @@ RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries,
  * mbarrier); warps_per_query: warps of the CTA that owns a query (1..8); stage_rows: rows per warp staging buffer. */
 RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
                                      int hash_log2);
-/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA). */
+/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA);
+ * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
+ * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
+ * (default 3): 1 = L2-prefetch the adjacency row of the next unexpanded pool entry, 2 = of scored candidates that beat it. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Diagnostics (synchronises the device): queries of the last batch that were redone by the big-table visited-set pass. */
 RG_API uint32_t rg_search_last_overflow_count(rg_index *index);
@@ -110,7 +113,12 @@ RG_API rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_
                                      uint64_t nq, uint32_t K, int metric, uint32_t *d_ids, float *d_dists,
                                      int device, void *cuda_stream);
 
-/* Diagnostics of the last rg_knn_exact* call in this process: kernel launches issued, and how many queries
+/* Host-buffer variant of the K4 merge (H2D, kernel, D2H inside the call); part_ids/part_dists are [G][nq][K].  An id of
+ * 0xFFFFFFFF marks an empty slot (a part with fewer than K rows, or an entry dropped by the caller) and is skipped. */
+RG_API rg_status rg_knn_merge(const uint32_t *part_ids, const float *part_dists, uint32_t G, uint64_t nq, uint32_t K,
+                              int metric, uint32_t *ids, float *dists, int device);
+
+/* Diagnostics of the last rg_knn_exact* call of the calling thread: kernel launches issued, and how many queries
  * failed the completeness certificate and were redone by the exact FP32 scan. */
 RG_API void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans);
 
@@ -128,6 +136,11 @@ RG_API rg_status rg_build_roargraph_device(const float *d_base, uint64_t n, uint
                                            const uint32_t *d_knn_ids, uint64_t n_train, uint32_t knn_k, uint32_t M_sq,
                                            uint32_t M_pjbp, uint32_t L_pjpq, rg_graph **out, int device,
                                            void *cuda_stream);
+/* Host-buffer variant (what the drop-in IndexBipartite::BuildRoarGraph calls when Parameters holds "gpu_build" != 0):
+ * base and knn_ids are host memory; they are uploaded for the duration of the build. */
+RG_API rg_status rg_build_roargraph(const float *base, uint64_t n, uint32_t dim, int metric, const uint32_t *knn_ids,
+                                    uint64_t n_train, uint32_t knn_k, uint32_t M_sq, uint32_t M_pjbp, uint32_t L_pjpq,
+                                    rg_graph **out, int device);
 /* phase_seconds (may be NULL): 6 doubles = entry point, projection, reverse edges, enhancement searches,
  * enhancement prune + reverse edges, degree check + merge. */
 RG_API rg_status rg_graph_info(const rg_graph *graph, uint64_t *n, uint32_t *max_degree, uint64_t *nnz, uint32_t *ep,

@@ -21,8 +21,8 @@ METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
-           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device",
-           "rg_knn_last_stats", "rg_build_roargraph_device", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
+           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
+           "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
            "rg_index_create_from_graph"]
 
 _lib = None
@@ -70,6 +70,8 @@ def lib():
     L.rg_knn_exact_device.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, i32, vp]
     L.rg_knn_merge_device.restype = i32
     L.rg_knn_merge_device.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32, vp]
+    L.rg_knn_merge.restype = i32
+    L.rg_knn_merge.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32]
     L.rg_knn_last_stats.restype = None
     L.rg_knn_last_stats.argtypes = [vp, vp]
     L.rg_build_roargraph_device.restype = i32
@@ -141,9 +143,14 @@ class Index:
 
     __del__ = close
 
-    def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0):
+    def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0,
+                  l2_hint=None, adj_prefetch=None):
         _check(lib().rg_search_configure(self._h, gather, warps_per_query, ctas_per_sm, stage_rows, hash_log2))
         _check(lib().rg_search_set_option(self._h, b"hash_space", hash_space))
+        if l2_hint is not None:
+            _check(lib().rg_search_set_option(self._h, b"l2_hint", l2_hint))
+        if adj_prefetch is not None:
+            _check(lib().rg_search_set_option(self._h, b"adj_prefetch", adj_prefetch))
 
     @property
     def last_overflow(self) -> int:

@@ -710,6 +710,26 @@ rg_status rg_build_roargraph_device(const float *d_base, uint64_t n, uint32_t di
     return RG_OK;
 }
 
+// Host-buffer variant: uploads the base rows and the kNN ids, builds on the device, frees the uploads.
+rg_status rg_build_roargraph(const float *base, uint64_t n, uint32_t dim, int metric, const uint32_t *knn_ids, uint64_t n_train,
+                             uint32_t knn_k, uint32_t M_sq, uint32_t M_pjbp, uint32_t L_pjpq, rg_graph **out, int device) {
+    if (!base || !knn_ids || !out) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_roargraph: null argument");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    rg::build::Scratch sc;
+    float *d_base = nullptr;
+    uint32_t *d_knn = nullptr;
+    RG_CUDA_OK(sc.alloc(&d_base, n * uint64_t(dim)));
+    RG_CUDA_OK(sc.alloc(&d_knn, n_train * uint64_t(knn_k)));
+    RG_CUDA_OK(cudaMemcpy(d_base, base, n * uint64_t(dim) * sizeof(float), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMemcpy(d_knn, knn_ids, n_train * uint64_t(knn_k) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    rg_status s = rg_build_roargraph_device(d_base, n, dim, metric, d_knn, n_train, knn_k, M_sq, M_pjbp, L_pjpq, out, device, nullptr);
+    if (s != RG_OK) return s;
+    RG_CUDA_OK(cudaDeviceSynchronize());
+    return RG_OK;
+}
+
 rg_status rg_graph_info(const rg_graph *g, uint64_t *n, uint32_t *max_degree, uint64_t *nnz, uint32_t *ep, double *phase_seconds) {
     if (!g) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_graph_info: null graph");
     if (n) *n = g->n;

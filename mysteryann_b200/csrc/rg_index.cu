@@ -149,6 +149,7 @@ rg_status rg_index_destroy(rg_index *ix) {
     if (!ix) return RG_OK;
     rg::DeviceGuard guard(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->persist_bytes) cudaCtxResetPersistingL2Cache();  // the visited-hash slabs go away: demote their L2 lines
     if (ix->owns_base && ix->d_base) cudaFree(const_cast<float *>(ix->d_base));
     cudaFree(ix->d_adj);
     cudaFree(ix->d_counters);
@@ -203,6 +204,16 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
     if (!strcmp(name, "hash_space")) {
         if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory) or 2 (global memory)");
         ix->cfg_hash_space = value;
+        return RG_OK;
+    }
+    if (!strcmp(name, "l2_hint")) {
+        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..3");
+        ix->cfg_l2_hint = value;
+        return RG_OK;
+    }
+    if (!strcmp(name, "adj_prefetch")) {
+        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "adj_prefetch is a bit mask 0..3");
+        ix->cfg_adj_prefetch = value;
         return RG_OK;
     }
     return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: unknown option '%s'", name);

@@ -42,6 +42,9 @@ struct rg_index {
 
     // tuning (0 = auto)
     int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0, cfg_hash_space = 0;
+    int cfg_l2_hint = 3, cfg_adj_prefetch = 3;  // see SearchParams::l2_hint / adj_prefetch; measured best on B200
+                                                // (profiles/r01_k1_variants_10m.txt)
 
+    uint64_t persist_bytes = 0;  // persisting-L2 set-aside requested so far (l2_hint bit 1)
     uint64_t launches = 0;
 };

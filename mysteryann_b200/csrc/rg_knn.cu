@@ -1066,7 +1066,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
 }  // namespace knn
 }  // namespace rg
 
-static uint64_t g_knn_stats[2] = {0, 0};
+static thread_local uint64_t g_knn_stats[2] = {0, 0};  // per calling thread (one host thread per GPU in the tools)
 
 extern "C" {
 
@@ -1116,7 +1116,31 @@ rg_status rg_knn_merge_device(const uint32_t *d_part_ids, const float *d_part_di
     return RG_OK;
 }
 
-// launches / queries that needed the exact scan in the last rg_knn_exact* call of this process
+rg_status rg_knn_merge(const uint32_t *part_ids, const float *part_dists, uint32_t G, uint64_t nq, uint32_t K, int metric,
+                       uint32_t *ids, float *dists, int device) {
+    if (!part_ids || !part_dists || !ids || !dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_merge: null argument");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    if (nq == 0) return RG_OK;
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    rg::knn::Scratch sc;
+    uint32_t *d_pi = nullptr, *d_i = nullptr;
+    float *d_pd = nullptr, *d_d = nullptr;
+    const uint64_t part = uint64_t(G) * nq * K;
+    RG_CUDA_OK(sc.alloc(&d_pi, part));
+    RG_CUDA_OK(sc.alloc(&d_pd, part));
+    RG_CUDA_OK(sc.alloc(&d_i, nq * K));
+    RG_CUDA_OK(sc.alloc(&d_d, nq * K));
+    RG_CUDA_OK(cudaMemcpy(d_pi, part_ids, part * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMemcpy(d_pd, part_dists, part * sizeof(float), cudaMemcpyHostToDevice));
+    rg_status s = rg_knn_merge_device(d_pi, d_pd, G, nq, K, metric, d_i, d_d, device, nullptr);
+    if (s != RG_OK) return s;
+    RG_CUDA_OK(cudaMemcpy(ids, d_i, nq * K * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    RG_CUDA_OK(cudaMemcpy(dists, d_d, nq * K * sizeof(float), cudaMemcpyDeviceToHost));
+    return RG_OK;
+}
+
+// launches / queries that needed the exact scan in the last rg_knn_exact* call of the calling thread
 void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans) {
     if (launches) *launches = g_knn_stats[0];
     if (exact_scans) *exact_scans = g_knn_stats[1];

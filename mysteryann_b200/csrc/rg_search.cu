@@ -50,6 +50,9 @@ struct SearchParams {
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
     uint32_t fallback;         // 1 = second pass over overflow_list with the big global table
+    uint32_t l2_hint;          // bit 0: base-row gathers evict_first (bit 1, host side: visited-hash slabs persist in L2)
+    uint32_t adj_prefetch;     // bit 0: L2-prefetch the adjacency row of the next unexpanded pool entry at selection
+                               // time; bit 1: of every scored candidate that beats it (it will be expanded first)
     // build mode (kBuild, SearchProjectionGraphInternal src/index_bipartite.cpp:1279-1350): query w is base row
     // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
     uint32_t node_lo, exp_cap;
@@ -98,6 +101,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
     const uint32_t cpr = dim >> 2;  // 16-byte chunks per row
     const uint32_t L = p.L, BR = p.stage_rows, RS = p.row_stride;
     uint32_t mb_phase = 0;
+    const bool rows_evict_first = (p.l2_hint & 1u) != 0;
+    const bool pf_next = (p.adj_prefetch & 1u) != 0, pf_cand = (p.adj_prefetch & 2u) != 0;
+    const uint64_t pol_first = l2_policy_evict_first();
+    const uint32_t adj_row_bytes = p.adj_stride * 4u;
 
     if (kGather == 2) {
         if (lane == 0) {
@@ -108,14 +115,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
     __syncthreads();
 
     // Gathers and scores this warp's candidates s_cid[0..n); keys below `tail` are appended to the CTA-wide list.
-    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl) {
+    // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
+    // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
+    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key) {
         for (uint32_t c0 = 0; c0 < n; c0 += BR) {
             const uint32_t rows = min(BR, n - c0);
             if (kGather == 2) {
                 if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
                 __syncwarp();
-                for (uint32_t r = lane; r < rows; r += 32)
-                    bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
+                if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
+                    for (uint32_t r = lane; r < rows; r += 32)
+                        bulk_g2s_hint(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar, pol_first);
+                } else {
+                    for (uint32_t r = lane; r < rows; r += 32)
+                        bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
+                }
                 mbar_wait(s_mbar, mb_phase);
                 mb_phase ^= 1u;
             } else {
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 // NeighborPriorityQueue::insert rejects keys behind the last entry of a full pool (neighbor.h:151);
                 // the tail only tightens during a hop, so dropping them here is exact
                 const bool keep = valid && t == 0 && key < tail;
+                if (pf_cand && keep && key < next_key) bulk_prefetch_l2(p.adj + size_t(s_cid[c0 + rr]) * p.adj_stride, adj_row_bytes);
                 const uint32_t m = __ballot_sync(0xffffffffu, keep);
                 if (m) {
                     const uint32_t leader = __ffs(m) - 1;
@@ -198,7 +213,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 if (kBuild) visited_test_and_set(hash, p.hash_log2, p.ep);
             }
             __syncwarp();
-            gather_and_score(1, tail, kCtlHop0);
+            gather_and_score(1, tail, kCtlHop0, ~0ull);
         }
 
         for (;;) {
@@ -314,6 +329,27 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
             }
             const uint32_t deg = __ldg(row);
+            // speculation for the NEXT hop: the best unexpanded entry behind `cur` is expanded next unless a candidate of
+            // this hop beats it; request its adjacency row now (one bulk L2 prefetch per CTA)
+            uint64_t next_key = tail;
+            if (pf_next || pf_cand) {
+                uint32_t c = cur + 1, nx = size;
+                while (c < size) {
+                    const uint32_t i = c + lane;
+                    const bool unexp = (i < size) && ((P[i] & 1ull) == 0);
+                    const uint32_t m = __ballot_sync(0xffffffffu, unexp);
+                    if (m) {
+                        nx = c + (__ffs(m) - 1);
+                        break;
+                    }
+                    c += 32;
+                }
+                if (nx < size) {
+                    next_key = P[nx] & ~1ull;
+                    if (pf_next && warp == W - 1 && lane == 0)
+                        bulk_prefetch_l2(p.adj + size_t(key_id(next_key)) * p.adj_stride, adj_row_bytes);
+                }
+            }
             uint32_t n_w = 0;
             for (uint32_t it = 0; it * 32 * W < deg; ++it) {
                 const uint32_t j = (lane + 32 * it) * W + warp;
@@ -333,7 +369,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
                 // a re-scored entry point lands here too; the merge drops it as a duplicate (neighbor.h:161) or the tail
                 // test drops it (neighbor.h:151), exactly like the reference
-                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp);
+                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp, next_key);
             }
         }
 
@@ -431,6 +467,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || ix->cfg_hash_space != 1);
     p.fallback = fallback ? 1u : 0u;
+    p.l2_hint = uint32_t(ix->cfg_l2_hint);
+    p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
     // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
     g->global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
@@ -481,6 +519,40 @@ static rg_status ensure(void **ptr, uint64_t *cap, uint64_t want, size_t elem) {
     return RG_OK;
 }
 
+// Launches g.fn with an access-policy window that marks [ptr, ptr + bytes) as persisting in L2.  The persisting set-aside
+// is a device-wide limit; it is raised once per index to what the window needs (capped by the device maximum).
+static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
+                                               cudaStream_t st) {
+    int max_persist = 0, max_window = 0;
+    RG_CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device));
+    RG_CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device));
+    const uint64_t window = std::min<uint64_t>(bytes, uint64_t(max_window));
+    const uint64_t setaside = std::min<uint64_t>(window, uint64_t(max_persist));
+    if (setaside == 0) return rg::fail(RG_ERR_CUDA, "device has no persisting L2 set-aside");
+    if (ix->persist_bytes < setaside) {
+        RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(setaside)));
+        ix->persist_bytes = setaside;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(unsigned(g.warps * 32));
+    cfg.dynamicSmemBytes = g.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.id = cudaLaunchAttributeAccessPolicyWindow;
+    attr.val.accessPolicyWindow.base_ptr = ptr;
+    attr.val.accessPolicyWindow.num_bytes = size_t(window);
+    attr.val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(setaside) / double(window)));
+    attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    RG_CUDA_OK(cudaLaunchKernelEx(&cfg, g.fn, g.p));
+    return RG_OK;
+}
+
 // d_exp_keys != nullptr selects the build-time variant: the queries are base rows node_lo .. node_lo + nq - 1
 static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t L,
                                     uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops,
@@ -527,7 +599,13 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
         g->p.exp_cap = exp_cap;
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
-    g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
+    if (g1.global_hash && (ix->cfg_l2_hint & 2)) {
+        // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, (uint64_t(grid1) << g1.p.hash_log2) * sizeof(uint32_t), st);
+        if (s != RG_OK) return s;
+    } else {
+        g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
+    }
     RG_CUDA_OK(cudaGetLastError());
     ix->launches++;
     g2.fn<<<grid2, g2.warps * 32, g2.smem_bytes, st>>>(g2.p);  // exits immediately when nothing overflowed

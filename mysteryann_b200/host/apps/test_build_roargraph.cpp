@@ -10,12 +10,13 @@
 
 int main(int argc, char **argv) {
     std::string base_data_file, sampled_query_data_file, projection_index_save_file, learn_base_nn_file, data_type, dist;
-    uint32_t M_sq, M_pjbp, L_pjpq, num_threads;
+    uint32_t M_sq, M_pjbp, L_pjpq, num_threads, gpu_build;
     try {
         CliArgs args(argc, argv, {{"-T", "--num_threads"}, {"-h", "--help"}});
         if (args.has("help")) {
             std::cout << "Arguments: --data_type <float> --dist <l2/ip/cosine> --base_data_path F --sampled_query_data_path F\n"
-                         "  --projection_index_save_path F --learn_base_nn_path F [--M_sq 32] [--M_pjbp 32] [--L_pjpq 32] [-T threads]\n";
+                         "  --projection_index_save_path F --learn_base_nn_path F [--M_sq 32] [--M_pjbp 32] [--L_pjpq 32] [-T threads]\n"
+                         "  [--gpu_build 1]   (not in the reference: run the graph construction on the GPU)\n";
             return 0;
         }
         data_type = args.get<std::string>("data_type");
@@ -28,6 +29,7 @@ int main(int argc, char **argv) {
         M_pjbp = args.get<uint32_t>("M_pjbp", 32);
         L_pjpq = args.get<uint32_t>("L_pjpq", 32);
         num_threads = args.get<uint32_t>("num_threads", (uint32_t)omp_get_num_procs());
+        gpu_build = args.get<uint32_t>("gpu_build", 0);
     } catch (const std::exception &ex) {
         std::cerr << ex.what() << '\n';
         return -1;
@@ -61,6 +63,7 @@ int main(int argc, char **argv) {
     parameters.Set<uint32_t>("M_pjbp", M_pjbp);
     parameters.Set<uint32_t>("L_pjpq", L_pjpq);
     parameters.Set<uint32_t>("num_threads", num_threads);
+    parameters.Set<uint32_t>("gpu_build", gpu_build);
     index_bipartite.LoadLearnBaseKNN(learn_base_nn_file.c_str());
     omp_set_num_threads((int)num_threads);
     auto s = std::chrono::high_resolution_clock::now();

@@ -1,7 +1,7 @@
 // Drop-in for the reference's efanna2e::IndexBipartite (include/index_bipartite.h:23-171), restricted to the
 // RoarGraph path (tests/test_search_roargraph.cpp, tests/test_build_roargraph.cpp).  Same public names and
-// argument meaning; search runs on the GPU through the C ABI in include/roargraph_b200.h, graph construction
-// stays on the host CPU like the reference.  The legacy bipartite methods of the reference are out of scope.
+// argument meaning; search runs on the GPU through the C ABI in include/roargraph_b200.h; graph construction runs on
+// the host CPU like the reference (edge-identical at one thread) or, with Parameters "gpu_build" = 1, on the GPU.  The legacy bipartite methods of the reference are out of scope.
 #pragma once
 #include <cstdint>
 #include <mutex>
@@ -66,6 +66,7 @@ class IndexBipartite : public Index {
     // graph construction steps (see src/index_bipartite.cpp file:line in index_bipartite.cpp)
     void calculate_projection_ep();
     void link_projection(const Parameters &parameters);
+    void build_on_device(const Parameters &parameters);  // Parameters "gpu_build" != 0
 
     Index *initializer_;
     CompactGraph projection_graph_, supply_nbrs_, learn_base_knn_;

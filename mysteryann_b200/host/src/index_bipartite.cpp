@@ -484,6 +484,39 @@ void IndexBipartite::link_projection(const Parameters &parameters) {
     std::cout << "Connectivity enhancement time: " << std::chrono::duration<double>(t2 - t1).count() << std::endl;
 }
 
+// Parameters "gpu_build" != 0: all construction phases run on the GPU (rg_build_roargraph, csrc/rg_build.cu).  Same
+// rules, applied phase-wise to all nodes at once, so - like a multi-threaded reference build - the adjacency is not
+// edge-identical to the one-thread CPU build; recall parity is tested in tests/test_build_gpu.py.
+void IndexBipartite::build_on_device(const Parameters &parameters) {
+    const uint32_t M = parameters.Get<uint32_t>("M_pjbp");
+    const uint32_t L_pjpq = parameters.Get<uint32_t>("L_pjpq");
+    const uint32_t M_sq = parameters.Get<uint32_t>("M_sq");
+    size_t knn_k = learn_base_knn_.empty() ? 0 : learn_base_knn_[0].size();
+    for (size_t i = 0; i < nd_sq_; ++i) knn_k = std::min(knn_k, learn_base_knn_[i].size());
+    if (knn_k == 0) throw std::runtime_error("learn base knn file error");
+    std::vector<uint32_t> flat(nd_sq_ * knn_k);
+    for (size_t i = 0; i < nd_sq_; ++i) std::copy_n(learn_base_knn_[i].begin(), knn_k, flat.begin() + i * knn_k);
+    rg_graph *g = nullptr;
+    std::cout << "begin link projection (GPU " << device_ << ")" << std::endl;
+    if (rg_build_roargraph(data_bp_, nd_, (uint32_t)dimension_, rg_metric(metric_), flat.data(), nd_sq_, (uint32_t)knn_k, M_sq, M,
+                           L_pjpq, &g, device_) != RG_OK)
+        throw_rg("rg_build_roargraph");
+    uint64_t n = 0, nnz = 0;
+    uint32_t dmax = 0, ep = 0;
+    double phases[6];
+    if (rg_graph_info(g, &n, &dmax, &nnz, &ep, phases) != RG_OK) throw_rg("rg_graph_info");
+    std::vector<uint64_t> offsets(n + 1);
+    std::vector<uint32_t> adj(nnz);
+    const rg_status s = rg_graph_download(g, offsets.data(), adj.data());
+    rg_graph_destroy(g);
+    if (s != RG_OK) throw_rg("rg_graph_download");
+    projection_ep_ = ep;
+    projection_graph_.assign(nd_, {});
+    for (size_t i = 0; i < nd_; ++i) projection_graph_[i].assign(adj.begin() + offsets[i], adj.begin() + offsets[i + 1]);
+    std::cout << "GPU build phases (s): ep " << phases[0] << ", projection " << phases[1] << ", reverse " << phases[2]
+              << ", enhancement search " << phases[3] << ", enhancement prune " << phases[4] << ", merge " << phases[5] << std::endl;
+}
+
 // BuildRoarGraph, :143-233
 void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data,
                                     const Parameters &parameters) {
@@ -501,11 +534,15 @@ void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_
         float *data = const_cast<float *>(data_bp_);
         for (size_t i = 0; i < nd_; ++i) normalize(data + i * dimension_, dimension_);
     }
-    projection_graph_.assign(nd_, {});  // BipartiteProjectionReserveSpace :951-958
-    supply_nbrs_.assign(nd_, {});
-    calculate_projection_ep();
-    std::cout << "begin link projection" << std::endl;
-    link_projection(parameters);
+    if (parameters.Get<uint32_t>("gpu_build", 0u) != 0) {
+        build_on_device(parameters);
+    } else {
+        projection_graph_.assign(nd_, {});  // BipartiteProjectionReserveSpace :951-958
+        supply_nbrs_.assign(nd_, {});
+        calculate_projection_ep();
+        std::cout << "begin link projection" << std::endl;
+        link_projection(parameters);
+    }
     std::cout << std::endl;
     auto e = std::chrono::high_resolution_clock::now();
     std::cout << "Build projection graph time: " << std::chrono::duration<double>(e - s).count() << std::endl;

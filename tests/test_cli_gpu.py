@@ -1,0 +1,119 @@
+"""GPU tests of the three drop-in CLI drivers (mysteryann_b200/host/apps): compute_groundtruth, test_build_roargraph
+(--gpu_build) and test_search_roargraph, run as a user of the reference would run them, with the CPU oracle as checker.
+Reference drivers: thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp, tests/test_build_roargraph.cpp,
+tests/test_search_roargraph.cpp."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_knn_gpu import check_knn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bins():
+    from mysteryann_b200 import build, hostlib
+
+    build.build()
+    hostlib.build()
+    return hostlib.BIN_DIR
+
+
+def run(cmd):
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, f"{' '.join(cmd)}\n{p.stdout[-2000:]}\n{p.stderr[-2000:]}"
+    return p.stdout
+
+
+def pad8(x):
+    from mysteryann_b200 import io
+
+    return io.pad_rows(x, 8)
+
+
+@pytest.mark.parametrize("dist_fn,metric", [("mips", 1), ("l2", 0)])
+def test_compute_groundtruth_parts_and_format(bins, oracle, tmp_path, dist_fn, metric):
+    """3 base parts (--part_size), unpadded D=100 rows, K=20: file = i32 n, i32 K, u32 ids, f32 dists (IP as +ip)."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(7)
+    base = rng.standard_normal((6000, 100)).astype(np.float32)
+    q = rng.standard_normal((150, 100)).astype(np.float32)
+    io.write_fbin(tmp_path / "base.fbin", base)
+    io.write_fbin(tmp_path / "q.fbin", q)
+    out = run([os.path.join(bins, "compute_groundtruth"), "--data_type", "float", "--dist_fn", dist_fn, "--base_file",
+               str(tmp_path / "base.fbin"), "--query_file", str(tmp_path / "q.fbin"), "--gt_file", str(tmp_path / "gt.bin"),
+               "--K", "20", "--part_size", "2500"])
+    assert "Number of parts: 3" in out
+    raw = np.fromfile(tmp_path / "gt.bin", dtype=np.uint8)
+    assert raw.size == 8 + 150 * 20 * 8
+    assert tuple(raw[:8].view(np.int32)) == (150, 20)
+    ids, dists = io.read_ibin(tmp_path / "gt.bin")
+    want_ids, want_d, _ = oracle.exact_knn(pad8(base), pad8(q), 20, metric=metric)
+    check_knn(ids, dists, want_ids, want_d, f"cli {dist_fn}")
+
+
+def test_compute_groundtruth_cosine_and_uint8(bins, tmp_path):
+    """cosine = L2 on normalised rows (compute_groundtruth.cpp:146-175); uint8 input is converted like load_bin_as_float."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(8)
+    base = rng.integers(0, 255, (3000, 64)).astype(np.uint8)
+    q = rng.integers(0, 255, (64, 64)).astype(np.uint8)
+    for name, x in (("base.u8bin", base), ("q.u8bin", q)):
+        with open(tmp_path / name, "wb") as f:
+            np.array(x.shape, np.int32).tofile(f)
+            x.tofile(f)
+    run([os.path.join(bins, "compute_groundtruth"), "--data_type", "uint8", "--dist_fn", "cosine", "--base_file",
+         str(tmp_path / "base.u8bin"), "--query_file", str(tmp_path / "q.u8bin"), "--gt_file", str(tmp_path / "gt.bin"), "--K", "10"])
+    ids, dists = io.read_ibin(tmp_path / "gt.bin")
+    b = base.astype(np.float64)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    qq = q.astype(np.float64)
+    qq /= np.linalg.norm(qq, axis=1, keepdims=True)
+    d = ((qq[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(d, axis=1, kind="stable")[:, :10]
+    want_d = np.take_along_axis(d, order, 1)
+    assert np.allclose(dists, want_d, rtol=1e-4, atol=2e-6)
+    agree = np.mean([len(set(a) & set(b_)) / 10 for a, b_ in zip(ids.tolist(), order.tolist())])
+    assert agree > 0.995   # only FP32 near-ties may differ from the FP64 ranking
+
+
+def test_pipeline_knn_build_search(bins, oracle, tmp_path):
+    """The reference's workflow end to end on the GPU: learn->base kNN, RoarGraph build (--gpu_build), test ground truth,
+    L sweep; the CSV row of every L must equal what the CPU oracle computes on the index file the build wrote."""
+    from mysteryann_b200 import io, synth
+
+    base, train, test = synth.make_numpy(20000, 20000, 500, 200, seed=11)
+    for name, x in (("base.fbin", base), ("train.fbin", train), ("test.fbin", test)):
+        io.write_fbin(tmp_path / name, x)
+    gt_tool = os.path.join(bins, "compute_groundtruth")
+    run([gt_tool, "--data_type", "float", "--dist_fn", "mips", "--base_file", str(tmp_path / "base.fbin"), "--query_file",
+         str(tmp_path / "train.fbin"), "--gt_file", str(tmp_path / "train.gt.bin"), "--K", "100"])
+    run([gt_tool, "--data_type", "float", "--dist_fn", "mips", "--base_file", str(tmp_path / "base.fbin"), "--query_file",
+         str(tmp_path / "test.fbin"), "--gt_file", str(tmp_path / "test.gt.bin"), "--K", "100"])
+    out = run([os.path.join(bins, "test_build_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path",
+               str(tmp_path / "base.fbin"), "--sampled_query_data_path", str(tmp_path / "train.fbin"),
+               "--projection_index_save_path", str(tmp_path / "rg.index"), "--learn_base_nn_path", str(tmp_path / "train.gt.bin"),
+               "--M_sq", "100", "--M_pjbp", "35", "--L_pjpq", "500", "--gpu_build", "1"])
+    assert "GPU build phases" in out
+    Ls = [10, 20, 50, 100]
+    run([os.path.join(bins, "test_search_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path",
+         str(tmp_path / "base.fbin"), "--query_path", str(tmp_path / "test.fbin"), "--gt_path", str(tmp_path / "test.gt.bin"),
+         "--projection_index_save_path", str(tmp_path / "rg.index"), "--k", "10", "--evaluation_save_path", str(tmp_path / "eval.csv"),
+         "--L_pq"] + [str(L) for L in Ls])
+    rows = [line.strip().split(",") for line in open(tmp_path / "eval.csv") if line.strip()]
+    assert [int(r[0]) for r in rows] == Ls and all(len(r) == 6 for r in rows)
+    ep, off, adj = io.read_index(tmp_path / "rg.index")
+    gt_ids, _ = io.read_ibin(tmp_path / "test.gt.bin")
+    for r in rows:
+        L = int(r[0])
+        want = oracle.search(base, off, adj, ep, test, 10, L, metric=1)
+        recall = oracle.recall(want["ids"], gt_ids, 10)
+        assert abs(float(r[4]) - recall) < 1e-5, (L, r, recall)
+        assert abs(float(r[2]) - want["cmps"].mean()) < 1e-2 * max(1.0, want["cmps"].mean() * 1e-3), (L, r)
+        assert abs(float(r[5]) - want["hops"].mean()) < 1e-2, (L, r)
+    assert float(rows[-1][4]) > 0.9   # the GPU-built graph is a working RoarGraph

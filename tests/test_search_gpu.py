@@ -39,22 +39,24 @@ def capi():
     return capi
 
 
-# (gather, warps per query, visited-hash space): cp.async / TMA bulk gathers, 1..8 warps per query, shared / global hash
-CONFIGS = ((2, 4, 2), (1, 4, 2), (2, 1, 1), (2, 2, 2), (1, 3, 1), (2, 8, 2))
+# (gather, warps per query, visited-hash space, L2 hints, adjacency prefetch): cp.async / TMA bulk gathers, 1..8 warps per
+# query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch
+CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 2, 0, 0), (2, 1, 1, 0, 0), (2, 2, 2, 3, 3), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2),
+           (2, 2, 2, 2, 1), (2, 2, 2, 0, 0))
 
 
-@pytest.mark.parametrize("gather,warps,space", CONFIGS)
+@pytest.mark.parametrize("gather,warps,space,l2,pf", CONFIGS)
 @pytest.mark.parametrize("name", CASES)
-def test_golden(capi, name, gather, warps, space):
+def test_golden(capi, name, gather, warps, space, l2, pf):
     c = load_case(name)
     ix = capi.Index(c["base"], c["offsets"], c["adj"], c["ep"], metric=c["metric"])
-    ix.configure(gather=gather, warps_per_query=warps, hash_space=space)
+    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf)
     for L in c["Ls"]:
         L = int(L)
         got = ix.search(c["test"], 10, L)
         assert got["rc"] == 0
         want = {k: c[f"{k}_{L}"] for k in ("ids", "dists", "cmps", "hops")}
-        report(f"{name} L={L} gather={gather} warps={warps} space={space}", got, want)
+        report(f"{name} L={L} gather={gather} warps={warps} space={space} l2={l2} pf={pf}", got, want)
     ix.close()
 
 
@@ -80,8 +82,8 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     if off[ep + 1] == off[ep]:
         ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    for gather, warps, space in CONFIGS[:4]:
-        ix.configure(gather=gather, warps_per_query=warps, hash_space=space)
+    for gather, warps, space, l2, pf in CONFIGS[:5]:
+        ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf)
         for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
             want = oracle.search(base, off, adj, ep, q, k, L, metric=metric)
             got = ix.search(q, k, L)

@@ -37,9 +37,10 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     rows = []
     for cfg in a.configs.split(","):
-        f = [int(v) for v in cfg.split(":")] + [0] * 6
-        gather, warps, ctas, stage, ghash, bufs = f[:6]
-        ix.configure(gather=gather, warps_per_query=warps, ctas_per_sm=ctas, stage_rows=stage, hash_space=ghash)
+        f = [int(v) for v in cfg.split(":")] + [0] * 7
+        gather, warps, ctas, stage, ghash, l2, pf = f[:7]
+        ix.configure(gather=gather, warps_per_query=warps, ctas_per_sm=ctas, stage_rows=stage, hash_space=ghash,
+                     l2_hint=l2, adj_prefetch=pf)
         for L in a.Ls:
             for _ in range(2):
                 ix.search_device(q, k, L, ids, dists, cmps, hops, None, st)
@@ -53,7 +54,7 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             c = float(cmps.sum().item()); h = float(hops.sum().item())
             gbs = c * a.dim * 4 / (ms * 1e-3) / 1e9
-            row = dict(gather=gather, warps=warps, ctas=ctas, stage=stage, hash_space=ghash, L=L, ms=round(ms, 3),
+            row = dict(gather=gather, warps=warps, ctas=ctas, stage=stage, hash_space=ghash, l2_hint=l2, adj_prefetch=pf, L=L, ms=round(ms, 3),
                        qps=round(a.nq / ms * 1e3), mean_cmps=c / a.nq, mean_hops=h / a.nq, gathered_GBs=round(gbs, 1))
             rows.append(row)
             print(json.dumps(row), flush=True)
