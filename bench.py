@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
     ap.add_argument("--adj-prefetch", type=int, default=None, help="K1 adjacency prefetch bit mask (None = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--normalize", action="store_true", help="L2-normalise all rows (CLIP-like config C3: --n 2500000 --dim 512)")
     return ap.parse_args()
 
 
@@ -88,8 +89,9 @@ def prepare(args, rank, world, device):
     from mysteryann_b200 import capi, io, synth
 
     n_train = args.train or max(50_000, args.n // 5)
-    base, train, test = synth.make_torch(args.n, n_train, args.queries * world, args.dim, seed=args.seed, device=device)
-    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}_gpu"
+    base, train, test = synth.make_torch(args.n, n_train, args.queries * world, args.dim, seed=args.seed, device=device,
+                                         normalize=args.normalize)
+    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}_gpu" + ("_unit" if args.normalize else "")
     os.makedirs(args.cache, exist_ok=True)
     index_path = os.path.join(args.cache, tag + ".index")
     info = {"n_train": n_train, "index_cached": os.path.exists(index_path), "builder": "rg_build_roargraph_device (GPU)"}
@@ -396,7 +398,7 @@ class CpuReference:
         if ref_available():
             self.kind, self.r = "reference", Ref()
             self.threads = self.r.num_procs()
-            fb = os.path.join(args.cache, f"base_n{args.n}_d{args.dim}_s{args.seed}.fbin")
+            fb = os.path.join(args.cache, f"base_n{args.n}_d{args.dim}_s{args.seed}{'_unit' if args.normalize else ''}.fbin")
             if not os.path.exists(fb):
                 io.write_fbin(fb + ".tmp", d["base"].cpu().numpy())
                 os.replace(fb + ".tmp", fb)

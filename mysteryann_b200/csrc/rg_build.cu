@@ -21,6 +21,7 @@
 // by (distance, id), de-duplicated, then walked in order; a candidate is kept unless some kept member r has
 // dist(candidate, r) < dist(candidate, owner) ("occluded").  Kept rows live in shared memory; candidate rows arrive in
 // batches of 8 by TMA bulk copies.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -605,6 +606,10 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     view.d_adj = S;
     view.sm_count = sms;
     view.max_smem_optin = smem_max;
+    // K1 cache hints for the build searches (tools/microbench_build.py measures the combinations)
+    if (const char *e = std::getenv("RG_BUILD_L2_HINT")) view.cfg_l2_hint = atoi(e) & 3;
+    if (const char *e = std::getenv("RG_BUILD_ADJ_PREFETCH")) view.cfg_adj_prefetch = atoi(e) & 3;
+    if (const char *e = std::getenv("RG_BUILD_WARPS")) view.cfg_warps = std::max(1, std::min(8, atoi(e)));
     RG_CUDA_OK(sc.alloc(&view.d_counters, 64));
     RG_CUDA_OK(cudaMemsetAsync(view.d_counters, 0, 64 * sizeof(uint32_t), st));
     pp.exp_keys = exp_keys;

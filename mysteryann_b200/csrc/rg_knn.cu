@@ -220,18 +220,42 @@ __device__ __forceinline__ void build_tree(const uint32_t (&v)[32], const float 
     t.b[3] = fmaxf(t.a[9], t.a[10]);
     t.m = fmaxf(max3(t.b[0], t.b[1], t.b[2]), t.b[3]);
 }
-// a lane whose staging slots are full appends directly (dense first blocks only)
-__device__ __noinline__ void direct_append(uint32_t *count, uint64_t *my_cand, uint64_t key) {
-    const uint32_t pos = atomicAdd(count, 1u);
-    if (pos < kCap) my_cand[pos] = key;
+// Dense path (first blocks, where a large share of the scores still beats the threshold): the lane's hits of this
+// accumulator slice are counted first, ONE returning atomic reserves room for all of them, then predicated stores
+// write the keys.  A returning atomic per hit (~700 cycles, and one divergent program position per column) made the
+// small early blocks cost ~0.4 ms each regardless of their size.
+template <bool kL2>
+__device__ __forceinline__ void bulk_append(const uint32_t (&v)[32], const float *bn, float half_scale, float theta,
+                                         float inv_scale, uint64_t row_first, uint64_t n_valid, uint32_t n_hits,
+                                         uint32_t *count, uint64_t *my_cand) {
+    uint32_t pos = atomicAdd(count, n_hits);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const uint64_t row = row_first + i;
+        if (filt<kL2>(v[i], bn, i, half_scale) > theta && row < n_valid) {
+            const float a = __uint_as_float(v[i]);
+            const float sc = kL2 ? fmaf(-2.f * inv_scale, a, bn[i]) : -(a * inv_scale);
+            if (pos < kCap) my_cand[pos] = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
+            ++pos;
+        }
+    }
 }
-// Hit path of one lane: walk the max tree down to the columns that beat the threshold and STAGE them in the lane's
-// shared-memory slots st[j * 32] (j < kStageSlots).  Nothing here waits on global memory: a returning atomic per hit
-// (~700 cycles) in one of the pair's 16 epilogue warps would delay the accumulator hand-back of the whole pair.
+template <bool kL2>
+__device__ __forceinline__ uint32_t count_hits(const uint32_t (&v)[32], const float *bn, float half_scale, float theta,
+                                               uint64_t row_first, uint64_t n_valid) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) n += (filt<kL2>(v[i], bn, i, half_scale) > theta && row_first + i < n_valid) ? 1u : 0u;
+    return n;
+}
+// Sparse path of one lane (at most kStageSlots - n_st hits, checked by the caller): walk the max tree down to the columns
+// that beat the threshold and STAGE them in the lane's shared-memory slots st[j * 32] (j < kStageSlots).  Nothing here
+// waits on global memory: a returning atomic in one of the pair's 16 epilogue warps would delay the accumulator hand-back
+// of the whole pair.
 template <bool kL2>
 __device__ __forceinline__ uint32_t stage_hits(const MaxTree &t, const uint32_t (&v)[32], const float *bn, float half_scale,
                                                float theta, float inv_scale, uint64_t row_first, uint64_t n_valid, uint64_t *st,
-                                               uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
+                                               uint32_t n_st) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (t.b[g] > theta) {
@@ -244,14 +268,9 @@ __device__ __forceinline__ uint32_t stage_hits(const MaxTree &t, const uint32_t 
                             const uint64_t row = row_first + i;
                             const float a = __uint_as_float(v[i]);
                             const float sc = kL2 ? fmaf(-2.f * inv_scale, a, bn[i]) : -(a * inv_scale);
-                            if (row < n_valid) {
-                                const uint64_t key = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
-                                if (n_st < kStageSlots) {
-                                    st[n_st * 32] = key;
-                                    ++n_st;
-                                } else {
-                                    direct_append(count, my_cand, key);
-                                }
+                            if (row < n_valid && n_st < kStageSlots) {
+                                st[n_st * 32] = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
+                                ++n_st;
                             }
                         }
                     }
@@ -259,6 +278,17 @@ __device__ __forceinline__ uint32_t stage_hits(const MaxTree &t, const uint32_t 
             }
         }
     }
+    return n_st;
+}
+// hits of one 32-column accumulator slice of this lane: few -> staged in shared memory, many -> one bulk reservation
+template <bool kL2>
+__device__ __forceinline__ uint32_t take_hits(const MaxTree &t, const uint32_t (&v)[32], const float *bn, float half_scale,
+                                              float theta, float inv_scale, uint64_t row_first, uint64_t n_valid, uint64_t *st,
+                                              uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
+    const uint32_t n_hits = count_hits<kL2>(v, bn, half_scale, theta, row_first, n_valid);
+    if (n_hits + n_st <= kStageSlots)
+        return stage_hits<kL2>(t, v, bn, half_scale, theta, inv_scale, row_first, n_valid, st, n_st);
+    bulk_append<kL2>(v, bn, half_scale, theta, inv_scale, row_first, n_valid, n_hits, count, my_cand);
     return n_st;
 }
 // one reservation per lane for everything it staged, then the copies
@@ -464,12 +494,12 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     MaxTree t;
                     build_tree<kL2>(v0, bn, half_scale, t);
                     if (t.m > theta)  // rare per lane: a few candidates per query per block
-                        n_st = stage_hits<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st, n_st,
-                                               p.cand_count + q, my_cand);
+                        n_st = take_hits<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st, n_st,
+                                              p.cand_count + q, my_cand);
                     build_tree<kL2>(v1, bn + 32, half_scale, t);
                     if (t.m > theta)
-                        n_st = stage_hits<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32, p.n_valid, st, n_st,
-                                               p.cand_count + q, my_cand);
+                        n_st = take_hits<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32, p.n_valid, st, n_st,
+                                              p.cand_count + q, my_cand);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -521,12 +551,17 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
     return p;
 }
 
-// K2s: one warp per query: keep the best kprime candidates (ascending), tighten tau, flag overflow
-__global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_t *cand_count, float *thr,
+// K2s: one warp per query: keep the best kprime candidates (ascending), tighten tau, flag overflow.
+// The list is [sorted survivors of the previous select (sorted_cnt of them) | hits appended since]: only the new hits
+// are sorted (bitonic, usually 128-256 keys instead of 512), then every key's position in the union follows from its
+// own index plus a binary search in the other run (keys are unique: one per base row), and the first kprime positions
+// are written back in order.
+constexpr uint32_t kSelSlots = kCap + 256;  // shared-memory keys per warp: survivors (<= 256) + power-of-two padded new run
+__global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_t *cand_count, uint32_t *sorted_cnt, float *thr,
                                                           uint32_t *overflow, uint32_t nq, uint32_t kprime) {
     extern __shared__ __align__(16) unsigned char sm[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *s = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * kCap;
+    uint64_t *sa = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * kSelSlots;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
     if (q >= nq) return;
     uint32_t n = cand_count[q];
@@ -534,17 +569,44 @@ __global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_
         if (lane == 0) overflow[q] = 1;
         n = kCap;
     }
-    if (n <= kprime && n != kCap) return;  // nothing to drop (tau stays)
+    if (n <= kprime && n != kCap) return;  // nothing to drop (tau stays; the sorted prefix is untouched)
     uint64_t *list = cand + uint64_t(q) * kCap;
-    const uint32_t P = next_pow2(n);
-    for (uint32_t i = lane; i < P; i += 32) s[i] = (i < n) ? list[i] : ~0ull;
+    const uint32_t na = min(sorted_cnt[q], n), nb = n - na;
+    uint64_t *sb = sa + na;
+    const uint32_t P = next_pow2(nb);
+    for (uint32_t i = lane; i < na; i += 32) sa[i] = list[i];
+    for (uint32_t i = lane; i < P; i += 32) sb[i] = (i < nb) ? list[na + i] : ~0ull;
     __syncwarp();
-    warp_bitonic_sort(s, P, lane);
+    warp_bitonic_sort(sb, P, lane);
     const uint32_t keep = min(n, kprime);
-    for (uint32_t i = lane; i < keep; i += 32) list[i] = s[i];
+    // position in the union = own index + number of smaller keys in the other run
+    for (uint32_t i = lane; i < na; i += 32) {
+        const uint64_t key = sa[i];
+        uint32_t lo = 0, hi = nb;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sb[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        const uint32_t pos = i + lo;
+        if (pos < keep) list[pos] = key;
+        if (pos == keep - 1 && keep == kprime) thr[q] = ordered_to_float(uint32_t(key >> 32));
+    }
+    for (uint32_t j = lane; j < nb; j += 32) {
+        const uint64_t key = sb[j];
+        uint32_t lo = 0, hi = na;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sa[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        const uint32_t pos = j + lo;
+        if (pos < keep) list[pos] = key;
+        if (pos == keep - 1 && keep == kprime) thr[q] = ordered_to_float(uint32_t(key >> 32));
+    }
     if (lane == 0) {
         cand_count[q] = keep;
-        if (keep == kprime) thr[q] = ordered_to_float(uint32_t(s[kprime - 1] >> 32));
+        sorted_cnt[q] = keep;
     }
 }
 
@@ -875,7 +937,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     Scratch sc;
     __half *b16 = nullptr, *q16 = nullptr, *b16t = nullptr, *q16t = nullptr;
     float *bnorm = nullptr, *thr = nullptr;
-    uint32_t *scal = nullptr, *cand_count = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
+    uint32_t *scal = nullptr, *cand_count = nullptr, *sorted_cnt = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
     uint64_t *cand = nullptr;
     RG_CUDA_OK(sc.alloc(&b16, uint64_t(n_full) * b_rows_pad * kSlabK));
     RG_CUDA_OK(sc.alloc(&q16, uint64_t(n_full) * q_rows_pad * kSlabK));
@@ -886,6 +948,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(sc.alloc(&scal, 8));
     RG_CUDA_OK(sc.alloc(&cand_count, q_batch));
     RG_CUDA_OK(sc.alloc(&overflow, q_batch));
+    RG_CUDA_OK(sc.alloc(&sorted_cnt, q_batch));
     RG_CUDA_OK(sc.alloc(&need_exact, q_batch));
     RG_CUDA_OK(sc.alloc(&flag_list, q_batch));
     RG_CUDA_OK(sc.alloc(&cand, q_batch * kCap));
@@ -973,7 +1036,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             cache.emplace_back(key, max_pairs);
         }
     }
-    RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSelSlots * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     const size_t scan_smem = (8 * 256 + 1024) * 8;
@@ -989,6 +1052,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
         RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
         RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
+        RG_CUDA_OK(cudaMemsetAsync(sorted_cnt, 0, bq * sizeof(uint32_t), st));
         launches += 2;
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
@@ -1021,7 +1085,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
             if (ip) knn_gemm_filter_kernel<false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
             else knn_gemm_filter_kernel<true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-            knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(cand, cand_count, thr, overflow, bq, kprime);
+            knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kSelSlots * 8, st>>>(cand, cand_count, sorted_cnt, thr, overflow, bq, kprime);
             launches += 2;
             lo = hi;
             len = std::max<uint64_t>(len, lo);  // next block as large as everything seen so far

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "rg_distance.cuh"
 #include "rg_index.cuh"
@@ -519,19 +520,32 @@ static rg_status ensure(void **ptr, uint64_t *cap, uint64_t want, size_t elem) {
     return RG_OK;
 }
 
-// Launches g.fn with an access-policy window that marks [ptr, ptr + bytes) as persisting in L2.  The persisting set-aside
-// is a device-wide limit; it is raised once per index to what the window needs (capped by the device maximum).
+// Launches g.fn with an access-policy window that marks [ptr, ptr + bytes) as persisting in L2.  Only used when the whole
+// window fits the device's persisting set-aside: pinning a random fraction of slabs that are larger than L2 anyway (the
+// L_pjpq = 500 build searches: 256 KB per CTA) only takes cache away from the adjacency rows - measured 38 s -> 55 s
+// for the 10M connectivity-enhancement searches.  The set-aside is a device-wide limit; it follows the window size.
+static bool persisting_window_fits(const rg_index *ix, uint64_t bytes) {
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return bytes > 0 && bytes <= uint64_t(max_persist) && bytes <= uint64_t(max_window);
+}
+
 static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
                                                cudaStream_t st) {
-    int max_persist = 0, max_window = 0;
-    RG_CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device));
-    RG_CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device));
-    const uint64_t window = std::min<uint64_t>(bytes, uint64_t(max_window));
-    const uint64_t setaside = std::min<uint64_t>(window, uint64_t(max_persist));
-    if (setaside == 0) return rg::fail(RG_ERR_CUDA, "device has no persisting L2 set-aside");
-    if (ix->persist_bytes < setaside) {
-        RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(setaside)));
-        ix->persist_bytes = setaside;
+    {   // device-wide limit shared by every index on the device
+        static std::mutex mu;
+        static uint64_t current[64] = {0};
+        std::lock_guard<std::mutex> lock(mu);
+        uint64_t &cur = current[ix->device & 63];
+        if (cur != bytes) {
+            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(bytes)));
+            cur = bytes;
+        }
+        ix->persist_bytes = bytes;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -543,8 +557,8 @@ static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, 
     memset(&attr, 0, sizeof(attr));
     attr.id = cudaLaunchAttributeAccessPolicyWindow;
     attr.val.accessPolicyWindow.base_ptr = ptr;
-    attr.val.accessPolicyWindow.num_bytes = size_t(window);
-    attr.val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(setaside) / double(window)));
+    attr.val.accessPolicyWindow.num_bytes = size_t(bytes);
+    attr.val.accessPolicyWindow.hitRatio = 1.0f;
     attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     cfg.attrs = &attr;
@@ -599,9 +613,10 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
         g->p.exp_cap = exp_cap;
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
-    if (g1.global_hash && (ix->cfg_l2_hint & 2)) {
+    const uint64_t slab_bytes = (uint64_t(grid1) << g1.p.hash_log2) * sizeof(uint32_t);
+    if (g1.global_hash && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
-        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, (uint64_t(grid1) << g1.p.hash_log2) * sizeof(uint32_t), st);
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, st);
         if (s != RG_OK) return s;
     } else {
         g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
