@@ -23,7 +23,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-L_SWEEP = [10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 35, 40, 45, 50, 60, 70, 80, 90, 100, 120, 150, 200, 300, 500]
+# the reference's own beam-width sweep (run_roargraph_search_test.sh:13), cut at 500 like BASELINE.json's "L sweep 10-500"
+L_SWEEP = [10, 15, 20, 25, 30, 35, 40, 45, 50, 55, 60, 65, 70, 75, 80, 85, 90, 95, 100, 110, 120, 130, 140, 150, 160, 170,
+           180, 190, 200, 220, 240, 260, 280, 300, 350, 400, 450, 500]
 
 
 def parse_args():
@@ -51,6 +53,7 @@ def parse_args():
     ap.add_argument("--hash-space", type=int, default=0)
     ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
     ap.add_argument("--adj-prefetch", type=int, default=None, help="K1 adjacency prefetch bit mask (None = library default)")
+    ap.add_argument("--zero-copy", type=int, default=1, help="e2e: 1 = rg_search_batch works in place on the pinned host buffers, 0 = staged copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--normalize", action="store_true", help="L2-normalise all rows (CLIP-like config C3: --n 2500000 --dim 512)")
     return ap.parse_args()
@@ -257,6 +260,7 @@ def run_ours(args):
     ix = d["index"]
     ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space,
                  l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch)
+    ix.set_option("zero_copy", args.zero_copy)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
     dists = torch.empty((nq, k), dtype=torch.float32, device=device)
@@ -370,7 +374,8 @@ def run_ours(args):
                        "ground_truth": "rg_knn_exact_device (exact, FP32 re-ranked)"},
             "e2e": {"value": round(nq * world / (e2e_ms / args.steps * 1e-3), 1), "unit": "queries/s",
                     "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 8 + 8,
-                    "api": "rg_search_batch (C ABI, pinned host buffers)"},
+                    "api": "rg_search_batch (C ABI, pinned host buffers; " + ("kernel reads queries / writes results in place over PCIe"
+                                                                                if args.zero_copy else "staged H2D + D2H copies") + ")"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": load_traffic(args, L_sel), "peak_kind": peak_kind,

@@ -68,7 +68,9 @@ RG_API rg_status rg_index_info(const rg_index *index, uint64_t *n, uint32_t *dim
  * IndexBipartite::SearchRoarGraph (src/index_bipartite.cpp:2311-2420) with L_pq = L:
  * ids[nq*k], dists[nq*k] (IP: negated dot; L2: squared distance), cmps[nq], hops[nq]
  * (cmps/hops may be NULL).  Results are bit-identical to the reference's.
- * Host variant: queries/results are host buffers; H2D, kernels and D2H happen inside the call.
+ * Host variant: queries/results are host buffers; H2D, kernels and D2H happen inside the call.  When every buffer
+ * passed is page-locked host memory (cudaHostAlloc / cudaHostRegister) the kernel reads the queries and writes
+ * the results through the mapped pointers (no staging copies); pageable buffers are staged ("zero_copy" option).
  * Returns RG_ERR_NOT_ENOUGH_RESULTS if any query ends with fewer than k pool entries (its ids
  * are filled with 0xFFFFFFFF), like the reference's std::runtime_error. */
 RG_API rg_status rg_search_batch(rg_index *index, const float *queries, uint64_t nq, uint32_t k, uint32_t L,
@@ -87,8 +89,14 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
 /* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA);
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
- * (default 3): 1 = L2-prefetch the adjacency row of the next unexpanded pool entry, 2 = of scored candidates that beat it. */
+ * (default 3): 1 = L2-prefetch the adjacency row of the next unexpanded pool entry, 2 = of scored candidates that beat it;
+ * "zero_copy" (default 1): rg_search_batch works straight on page-locked caller buffers, 0 = always stage through HBM. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
+/* Page-lock (and map) a caller-owned host buffer so that rg_search_batch can work on it without staging copies - what
+ * the drop-in driver does with the query array and result vectors it allocates (tests/test_search_roargraph.cpp:
+ * 166-179 in the reference).  Thin wrappers over cudaHostRegister / cudaHostUnregister. */
+RG_API rg_status rg_host_register(void *ptr, uint64_t bytes);
+RG_API rg_status rg_host_unregister(void *ptr);
 /* Diagnostics (synchronises the device): queries of the last batch that were redone by the big-table visited-set pass. */
 RG_API uint32_t rg_search_last_overflow_count(rg_index *index);
 /* Number of kernel launches issued by this library on behalf of `index` so far. */

@@ -21,7 +21,7 @@ METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
-           "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
+           "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
            "rg_index_create_from_graph"]
 
@@ -59,6 +59,10 @@ def lib():
     L.rg_search_configure.restype = i32
     L.rg_search_configure.argtypes = [vp, i32, i32, i32, i32, i32]
     L.rg_search_set_option.restype = i32
+    L.rg_host_register.restype = i32
+    L.rg_host_register.argtypes = [vp, C.c_uint64]
+    L.rg_host_unregister.restype = i32
+    L.rg_host_unregister.argtypes = [vp]
     L.rg_search_set_option.argtypes = [vp, C.c_char_p, i32]
     L.rg_search_last_overflow_count.restype = u32
     L.rg_search_last_overflow_count.argtypes = [vp]
@@ -151,6 +155,10 @@ class Index:
             _check(lib().rg_search_set_option(self._h, b"l2_hint", l2_hint))
         if adj_prefetch is not None:
             _check(lib().rg_search_set_option(self._h, b"adj_prefetch", adj_prefetch))
+
+    def set_option(self, name: str, value: int):
+        """Named option of rg_search_set_option ("hash_space", "l2_hint", "adj_prefetch", "zero_copy")."""
+        _check(lib().rg_search_set_option(self._h, name.encode(), int(value)))
 
     @property
     def last_overflow(self) -> int:

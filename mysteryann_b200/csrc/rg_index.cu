@@ -179,6 +179,31 @@ rg_status rg_index_info(const rg_index *ix, uint64_t *n, uint32_t *dim, int *met
     return RG_OK;
 }
 
+rg_status rg_host_register(void *ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_host_register: null argument");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return RG_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return rg::fail(RG_ERR_CUDA, "cudaHostRegister(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return RG_OK;
+}
+
+rg_status rg_host_unregister(void *ptr) {
+    if (!ptr) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_host_unregister: null argument");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return rg::fail(RG_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
+    return RG_OK;
+}
+
 uint64_t rg_index_launch_count(const rg_index *ix) { return ix ? ix->launches : 0; }
 
 rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
@@ -214,6 +239,11 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
     if (!strcmp(name, "adj_prefetch")) {
         if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "adj_prefetch is a bit mask 0..3");
         ix->cfg_adj_prefetch = value;
+        return RG_OK;
+    }
+    if (!strcmp(name, "zero_copy")) {
+        if (value < 0 || value > 1) return rg::fail(RG_ERR_INVALID_ARGUMENT, "zero_copy must be 0 (always stage) or 1 (direct when the caller buffers are page-locked)");
+        ix->cfg_zero_copy = value;
         return RG_OK;
     }
     return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: unknown option '%s'", name);

@@ -7,8 +7,8 @@
 //       operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle) in a ring of 64-wide K slabs; the epilogue reads
 //       the accumulators with tcgen05.ld and keeps only the scores that beat the query's current threshold
 //       (appended to a small per-query candidate list) - a threshold-filtered top-k' instead of a heap scan.
-//       The base is visited in blocks of doubling size; after each block K2s (one warp per query) sorts the list,
-//       keeps the best k' and tightens the threshold.
+//       The base is visited in blocks of doubling size; after each block K2s (one warp per query) finds the k'-th
+//       best score of the list by bisection, compacts the list to the entries at or below it and tightens the threshold.
 //   K3  FP32 re-rank of the k' survivors in the reference's lane-ordered arithmetic + a per-query CERTIFICATE:
 //       every point that is not a survivor has approx score >= tau (the worst survivor); the FP16 rounding error of a
 //       score is bounded by eps = 2^-10 |q| max|b| (x2 for L2), so if exact_K < tau - eps the top-K is provably
@@ -551,17 +551,13 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
     return p;
 }
 
-// K2s: one warp per query: keep the best kprime candidates (ascending), tighten tau, flag overflow.
-// The list is [sorted survivors of the previous select (sorted_cnt of them) | hits appended since]: only the new hits
-// are sorted (bitonic, usually 128-256 keys instead of 512), then every key's position in the union follows from its
-// own index plus a binary search in the other run (keys are unique: one per base row), and the first kprime positions
-// are written back in order.
-constexpr uint32_t kSelSlots = kCap + 256;  // shared-memory keys per warp: survivors (<= 256) + power-of-two padded new run
-__global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_t *cand_count, uint32_t *sorted_cnt, float *thr,
-                                                          uint32_t *overflow, uint32_t nq, uint32_t kprime) {
-    extern __shared__ __align__(16) unsigned char sm[];
+// K2s: one warp per query: keep the kprime best candidates, tighten tau, flag overflow.  No sorting (K3 re-scores and
+// sorts the survivors anyway): the kprime-th smallest score is found by bisection on its ordered 32-bit pattern with the
+// scores held in registers (32 probes, one redux.sync each), then the list is compacted in place to the entries at or
+// below it.  Equal scores stay together, so a list keeps a few more than kprime entries only on exact FP32 ties.
+__global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_t *cand_count, float *thr, uint32_t *overflow,
+                                                          uint32_t nq, uint32_t kprime) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *sa = reinterpret_cast<uint64_t *>(sm) + size_t(warp) * kSelSlots;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
     if (q >= nq) return;
     uint32_t n = cand_count[q];
@@ -569,44 +565,45 @@ __global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_
         if (lane == 0) overflow[q] = 1;
         n = kCap;
     }
-    if (n <= kprime && n != kCap) return;  // nothing to drop (tau stays; the sorted prefix is untouched)
+    if (n <= kprime) return;  // nothing to drop (tau stays)
     uint64_t *list = cand + uint64_t(q) * kCap;
-    const uint32_t na = min(sorted_cnt[q], n), nb = n - na;
-    uint64_t *sb = sa + na;
-    const uint32_t P = next_pow2(nb);
-    for (uint32_t i = lane; i < na; i += 32) sa[i] = list[i];
-    for (uint32_t i = lane; i < P; i += 32) sb[i] = (i < nb) ? list[na + i] : ~0ull;
-    __syncwarp();
-    warp_bitonic_sort(sb, P, lane);
-    const uint32_t keep = min(n, kprime);
-    // position in the union = own index + number of smaller keys in the other run
-    for (uint32_t i = lane; i < na; i += 32) {
-        const uint64_t key = sa[i];
-        uint32_t lo = 0, hi = nb;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sb[mid] < key) lo = mid + 1;
-            else hi = mid;
-        }
-        const uint32_t pos = i + lo;
-        if (pos < keep) list[pos] = key;
-        if (pos == keep - 1 && keep == kprime) thr[q] = ordered_to_float(uint32_t(key >> 32));
+    const uint32_t *hi_words = reinterpret_cast<const uint32_t *>(list) + 1;  // ordered(score) of entry i = hi_words[2 i]
+    constexpr uint32_t kPerLane = kCap / 32;
+    uint32_t sc[kPerLane];
+    const uint32_t nj = (n + 31) >> 5;
+#pragma unroll
+    for (uint32_t j = 0; j < kPerLane; ++j) {
+        const uint32_t i = j * 32 + lane;
+        sc[j] = (j < nj && i < n) ? hi_words[2 * i] : 0xFFFFFFFFu;  // padding is above every probe
     }
-    for (uint32_t j = lane; j < nb; j += 32) {
-        const uint64_t key = sb[j];
-        uint32_t lo = 0, hi = na;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sa[mid] < key) lo = mid + 1;
-            else hi = mid;
+    uint32_t lo = 0, hi = 0xFFFFFFFEu;  // smallest v with #{score <= v} >= kprime
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < kPerLane; ++j) {
+            if (j >= nj) break;  // warp-uniform
+            c += (sc[j] <= mid) ? 1u : 0u;
         }
-        const uint32_t pos = j + lo;
-        if (pos < keep) list[pos] = key;
-        if (pos == keep - 1 && keep == kprime) thr[q] = ordered_to_float(uint32_t(key >> 32));
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= kprime) hi = mid;
+        else lo = mid + 1;
+    }
+    const uint32_t v = lo;
+    // in-place compaction: round r reads entries [32r, 32r+32) and writes at most that many entries at positions
+    // <= 32r + 31, all of which were read in this or an earlier round (the ballot orders the reads before the writes)
+    uint32_t kept = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t key = (i < n) ? list[i] : ~0ull;
+        const bool keep = (i < n) && uint32_t(key >> 32) <= v;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[kept + __popc(m & lanemask_lt())] = key;
+        kept += __popc(m);
     }
     if (lane == 0) {
-        cand_count[q] = keep;
-        sorted_cnt[q] = keep;
+        cand_count[q] = kept;
+        thr[q] = ordered_to_float(v);
     }
 }
 
@@ -937,7 +934,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     Scratch sc;
     __half *b16 = nullptr, *q16 = nullptr, *b16t = nullptr, *q16t = nullptr;
     float *bnorm = nullptr, *thr = nullptr;
-    uint32_t *scal = nullptr, *cand_count = nullptr, *sorted_cnt = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
+    uint32_t *scal = nullptr, *cand_count = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
     uint64_t *cand = nullptr;
     RG_CUDA_OK(sc.alloc(&b16, uint64_t(n_full) * b_rows_pad * kSlabK));
     RG_CUDA_OK(sc.alloc(&q16, uint64_t(n_full) * q_rows_pad * kSlabK));
@@ -948,7 +945,6 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(sc.alloc(&scal, 8));
     RG_CUDA_OK(sc.alloc(&cand_count, q_batch));
     RG_CUDA_OK(sc.alloc(&overflow, q_batch));
-    RG_CUDA_OK(sc.alloc(&sorted_cnt, q_batch));
     RG_CUDA_OK(sc.alloc(&need_exact, q_batch));
     RG_CUDA_OK(sc.alloc(&flag_list, q_batch));
     RG_CUDA_OK(sc.alloc(&cand, q_batch * kCap));
@@ -1036,7 +1032,6 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             cache.emplace_back(key, max_pairs);
         }
     }
-    RG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSelSlots * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kCap * 8));
     const size_t scan_smem = (8 * 256 + 1024) * 8;
@@ -1052,7 +1047,6 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
         RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
         RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
-        RG_CUDA_OK(cudaMemsetAsync(sorted_cnt, 0, bq * sizeof(uint32_t), st));
         launches += 2;
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
@@ -1076,6 +1070,12 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         gp.n_stages = n_stages;
         // blocks of doubling size: [0,1024), [1024,2048), [2048,4096), ...  (tau = +inf in the first one: every score
         // of the first 1024 rows is kept, so the list can never overflow there)
+        // RG_KNN_GROWTH = g (2..8, default 2): a block is (g-1) x everything seen so far, i.e. ~(g-1) k' expected hits per query
+        static const uint64_t growth = [] {
+            const char *e = getenv("RG_KNN_GROWTH");
+            const long g = e ? atol(e) : 2;
+            return uint64_t(g < 2 ? 2 : (g > 8 ? 8 : g));
+        }();
         uint64_t lo = 0, len = kCap;
         while (lo < b_rows_pad) {
             const uint64_t hi = std::min(b_rows_pad, lo + len);
@@ -1085,10 +1085,10 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
             if (ip) knn_gemm_filter_kernel<false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
             else knn_gemm_filter_kernel<true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-            knn_select_kernel<<<(bq + 3) / 4, 128, 4 * kSelSlots * 8, st>>>(cand, cand_count, sorted_cnt, thr, overflow, bq, kprime);
+            knn_select_kernel<<<(bq + 3) / 4, 128, 0, st>>>(cand, cand_count, thr, overflow, bq, kprime);
             launches += 2;
             lo = hi;
-            len = std::max<uint64_t>(len, lo);  // next block as large as everything seen so far
+            len = std::max<uint64_t>(len, lo * (growth - 1));  // default: next block as large as everything seen so far
         }
         lap("  batch: gemm + select");
         if (ip)

@@ -669,12 +669,65 @@ uint32_t rg_search_last_overflow_count(rg_index *ix) {
     return v;
 }
 
+// Device-visible alias of a caller buffer when it is page-locked host memory (cudaHostAlloc / cudaHostRegister; under
+// unified addressing every such allocation is mapped), else nullptr.
+static void *mapped_alias(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
+
+static rg_status report_status(const uint32_t status[2], uint32_t k, uint32_t L) {
+    if (status[1]) return rg::fail(RG_ERR_INTERNAL, "visited set overflow in %u queries (L_pq=%u)", status[1], L);
+    if (status[0]) {
+        // report the first short query like the reference's message (src/index_bipartite.cpp:2408-2412)
+        return rg::fail(RG_ERR_NOT_ENOUGH_RESULTS, "not enough results: fewer than %u pool entries in %u queries, expected: %u", k, status[0], k);
+    }
+    return RG_OK;
+}
+
 rg_status rg_search_batch(rg_index *ix, const float *queries, uint64_t nq, uint32_t k, uint32_t L, uint32_t *ids,
                           float *dists, uint32_t *cmps, uint32_t *hops) {
     if (!ix || !queries || !ids || !dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_batch: null argument");
     if (nq == 0) return RG_OK;
     rg::DeviceGuard guard(ix->device);
     rg_status s;
+    cudaStream_t st = ix->stream;
+    uint32_t status[2] = {0, 0};
+    if (ix->stat_cap < nq + 2) {
+        cudaFree(ix->d_cmps);
+        cudaFree(ix->d_hops);
+        ix->d_cmps = ix->d_hops = nullptr;
+        ix->stat_cap = 0;
+        RG_CUDA_OK(cudaMalloc(&ix->d_cmps, (nq + 2) * sizeof(uint32_t)));
+        RG_CUDA_OK(cudaMalloc(&ix->d_hops, (nq + 2) * sizeof(uint32_t)));
+        ix->stat_cap = nq + 2;
+    }
+    uint32_t *d_status = ix->d_cmps + nq;  // two spare words behind the cmps array
+
+    // Zero-copy path: when every caller buffer is page-locked host memory the kernel reads each query (D floats, once,
+    // into shared memory) and writes each result row straight through the mapped pointers, so the host<->device
+    // transfers ride inside the search instead of in front of and behind it (8 MB in / 0.8 MB out per 10 000 queries
+    // at D=200, k=10: 2 GB/s against >50 GB/s of PCIe, hidden behind the HBM-bound gathers of the other resident queries).
+    if (ix->cfg_zero_copy) {
+        const float *zq = static_cast<const float *>(mapped_alias(queries));
+        uint32_t *zi = static_cast<uint32_t *>(mapped_alias(ids));
+        float *zd = static_cast<float *>(mapped_alias(dists));
+        uint32_t *zc = cmps ? static_cast<uint32_t *>(mapped_alias(cmps)) : nullptr;
+        uint32_t *zh = hops ? static_cast<uint32_t *>(mapped_alias(hops)) : nullptr;
+        if (zq && zi && zd && (!cmps || zc) && (!hops || zh)) {
+            s = rg::search_device(ix, zq, nq, k, L, zi, zd, zc, zh, d_status, st);
+            if (s != RG_OK) return s;
+            RG_CUDA_OK(cudaMemcpyAsync(status, d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            RG_CUDA_OK(cudaStreamSynchronize(st));
+            return report_status(status, k, L);
+        }
+    }
+
+    // Staged path (pageable caller buffers): H2D copy, search on index-owned device buffers, D2H copies.
     if ((s = rg::ensure((void **)&ix->d_queries, &ix->queries_cap, nq * ix->dim, sizeof(float))) != RG_OK) return s;
     if (ix->res_cap < nq * k) {
         cudaFree(ix->d_ids);
@@ -686,33 +739,16 @@ rg_status rg_search_batch(rg_index *ix, const float *queries, uint64_t nq, uint3
         RG_CUDA_OK(cudaMalloc(&ix->d_dists, nq * k * sizeof(float)));
         ix->res_cap = nq * k;
     }
-    if (ix->stat_cap < nq + 2) {
-        cudaFree(ix->d_cmps);
-        cudaFree(ix->d_hops);
-        ix->d_cmps = ix->d_hops = nullptr;
-        ix->stat_cap = 0;
-        RG_CUDA_OK(cudaMalloc(&ix->d_cmps, (nq + 2) * sizeof(uint32_t)));
-        RG_CUDA_OK(cudaMalloc(&ix->d_hops, (nq + 2) * sizeof(uint32_t)));
-        ix->stat_cap = nq + 2;
-    }
-    cudaStream_t st = ix->stream;
     RG_CUDA_OK(cudaMemcpyAsync(ix->d_queries, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-    uint32_t *d_status = ix->d_cmps + nq;  // two spare words behind the cmps array
     s = rg::search_device(ix, ix->d_queries, nq, k, L, ix->d_ids, ix->d_dists, ix->d_cmps, ix->d_hops, d_status, st);
     if (s != RG_OK) return s;
-    uint32_t status[2] = {0, 0};
     RG_CUDA_OK(cudaMemcpyAsync(ids, ix->d_ids, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA_OK(cudaMemcpyAsync(dists, ix->d_dists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (cmps) RG_CUDA_OK(cudaMemcpyAsync(cmps, ix->d_cmps, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (hops) RG_CUDA_OK(cudaMemcpyAsync(hops, ix->d_hops, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA_OK(cudaMemcpyAsync(status, d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA_OK(cudaStreamSynchronize(st));
-    if (status[1]) return rg::fail(RG_ERR_INTERNAL, "visited set overflow in %u queries (L_pq=%u)", status[1], L);
-    if (status[0]) {
-        // report the first short query like the reference's message (src/index_bipartite.cpp:2408-2412)
-        return rg::fail(RG_ERR_NOT_ENOUGH_RESULTS, "not enough results: fewer than %u pool entries in %u queries, expected: %u", k, status[0], k);
-    }
-    return RG_OK;
+    return report_status(status, k, L);
 }
 
 }  // extern "C"

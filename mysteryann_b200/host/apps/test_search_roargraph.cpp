@@ -10,10 +10,12 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cli_args.h"
 #include "index_bipartite.h"
+#include "roargraph_b200.h"
 
 // tests/test_search_roargraph.cpp:23-36
 static float ComputeRecall(uint32_t q_num, uint32_t k, uint32_t gt_dim, const uint32_t *res, const uint32_t *gt) {
@@ -99,6 +101,15 @@ int main(int argc, char **argv) {
     std::cout << "k: " << k << std::endl;
     std::vector<uint32_t> res((size_t)q_pts * k, 0), cmps(q_pts, 0), hops(q_pts, 0);
     std::vector<float> res_dists((size_t)q_pts * k, 0.f);
+    // page-lock the query and result arrays: rg_search_batch then reads/writes them in place (no staging copies)
+    const std::pair<void *, size_t> pinned[] = {{aligned_query_data, (size_t)q_pts * q_dim * sizeof(float)},
+                                                {res.data(), res.size() * sizeof(uint32_t)},
+                                                {res_dists.data(), res_dists.size() * sizeof(float)},
+                                                {cmps.data(), cmps.size() * sizeof(uint32_t)},
+                                                {hops.data(), hops.size() * sizeof(uint32_t)}};
+    for (const auto &b : pinned)
+        if (b.second && rg_host_register(b.first, b.second) != RG_OK)
+            std::cout << "note: buffer not page-locked (" << rg_last_error_string() << "), results are staged" << std::endl;
     std::ofstream evaluation_out;
     if (!evaluation_save_path.empty()) evaluation_out.open(evaluation_save_path, std::ios::out);
     std::cout << "Using GPU device: " << device << std::endl;
@@ -133,6 +144,8 @@ int main(int argc, char **argv) {
             evaluation_out << L_pq << "," << qps << "," << avg_cmps << "," << mean_latency_ms << "," << recall << ","
                            << avg_hops << std::endl;
     }
+    for (const auto &b : pinned)
+        if (b.second) rg_host_unregister(b.first);
     free(aligned_query_data);
     delete[] gt_ids;
     delete[] gt_dists;

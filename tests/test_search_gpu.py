@@ -163,3 +163,38 @@ def test_device_api_and_empty_batch(capi, oracle):
     assert ix.launches >= 3
     assert ix.search(np.zeros((0, 200), np.float32), 10, 32)["ids"].shape == (0, 10)
     ix.close()
+
+
+def test_pinned_host_buffers_zero_copy(capi):
+    """rg_search_batch on page-locked caller buffers (the kernel reads queries / writes results through the mapped
+    pointers), with and without the optional cmps/hops outputs, against the staged path and the golden vectors."""
+    import torch
+
+    c = load_case("ip_d200")
+    ix = capi.Index(c["base"], c["offsets"], c["adj"], c["ep"], metric=1)
+    hq = torch.from_numpy(c["test"]).pin_memory()
+    nq, k = hq.shape[0], 10
+    for L in (10, 100):
+        want = {k_: c[f"{k_}_{L}"] for k_ in ("ids", "dists", "cmps", "hops")}
+        for zero_copy in (1, 0):
+            ix.set_option("zero_copy", zero_copy)
+            ids = torch.full((nq, k), -1, dtype=torch.int32).pin_memory()
+            dists = torch.full((nq, k), 7.0, dtype=torch.float32).pin_memory()
+            cmps = torch.zeros(nq, dtype=torch.int32).pin_memory()
+            hops = torch.zeros(nq, dtype=torch.int32).pin_memory()
+            ix.search_raw(hq.data_ptr(), nq, k, L, ids.data_ptr(), dists.data_ptr(), cmps.data_ptr(), hops.data_ptr())
+            got = dict(ids=ids.numpy().view(np.uint32), dists=dists.numpy(), cmps=cmps.numpy().view(np.uint32),
+                       hops=hops.numpy().view(np.uint32))
+            report(f"pinned zero_copy={zero_copy} L={L}", got, want)
+            ids.fill_(-1)
+            ix.search_raw(hq.data_ptr(), nq, k, L, ids.data_ptr(), dists.data_ptr())  # no stats requested
+            assert (ids.numpy().view(np.uint32) == want["ids"]).all()
+    # mixed: pinned queries, pageable results -> staged path, same answer
+    ix.set_option("zero_copy", 1)
+    r_ids = np.empty((nq, k), np.uint32)
+    r_d = np.empty((nq, k), np.float32)
+    ix.search_raw(hq.data_ptr(), nq, k, 10, r_ids.ctypes.data, r_d.ctypes.data)
+    assert (r_ids == c["ids_10"]).all() and (bits(r_d) == bits(c["dists_10"])).all()
+    with pytest.raises(capi.RoarGraphError):
+        ix.set_option("zero_copy", 2)
+    ix.close()
