@@ -53,7 +53,6 @@ def parse_args():
     ap.add_argument("--hash-space", type=int, default=0)
     ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
     ap.add_argument("--adj-prefetch", type=int, default=None, help="K1 adjacency prefetch bit mask (None = library default)")
-    ap.add_argument("--drain", type=int, default=None, help="K1 drain pass share in percent of the resident CTAs (None = library default, 0 = off)")
     ap.add_argument("--zero-copy", type=int, default=1, help="e2e: 1 = rg_search_batch works in place on the pinned host buffers, 0 = staged copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--normalize", action="store_true", help="L2-normalise all rows (CLIP-like config C3: --n 2500000 --dim 512)")
@@ -262,8 +261,6 @@ def run_ours(args):
     ix.configure(gather=args.gather, warps_per_query=args.warps, stage_rows=args.stage_rows, hash_space=args.hash_space,
                  l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch)
     ix.set_option("zero_copy", args.zero_copy)
-    if args.drain is not None:
-        ix.set_option("drain", args.drain)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
     dists = torch.empty((nq, k), dtype=torch.float32, device=device)
@@ -385,7 +382,7 @@ def run_ours(args):
                          "kernel": "rg_search_kernel", "algorithmic_bytes_per_launch": int(alg_bytes)},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only; --impl reference times it at every N
+        if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, d, L_sel)
         print(json.dumps(out), flush=True)
     if world > 1:

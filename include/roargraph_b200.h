@@ -90,8 +90,6 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
  * (default 3): 1 = L2-prefetch the adjacency row of the next unexpanded pool entry, 2 = of scored candidates that beat it;
- * "drain" (default 60): share, in percent of the number of resident primary CTAs, of a large batch whose queries go to a
- * second grid of 8-warp CTAs launched programmatically dependent on the primary to fill the SMs during the batch's tail, 0 = off;
  * "zero_copy" (default 1): rg_search_batch works straight on page-locked caller buffers, 0 = always stage through HBM. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Page-lock (and map) a caller-owned host buffer so that rg_search_batch can work on it without staging copies - what

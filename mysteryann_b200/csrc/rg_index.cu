@@ -241,11 +241,6 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         ix->cfg_adj_prefetch = value;
         return RG_OK;
     }
-    if (!strcmp(name, "drain")) {
-        if (value < 0 || value > 200) return rg::fail(RG_ERR_INVALID_ARGUMENT, "drain is a percentage in [0, 200] (0 = no drain pass)");
-        ix->cfg_drain = value;
-        return RG_OK;
-    }
     if (!strcmp(name, "zero_copy")) {
         if (value < 0 || value > 1) return rg::fail(RG_ERR_INVALID_ARGUMENT, "zero_copy must be 0 (always stage) or 1 (direct when the caller buffers are page-locked)");
         ix->cfg_zero_copy = value;

@@ -27,7 +27,7 @@
 
 namespace rg {
 
-enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4, kCntWork3 = 5 };
+enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4 };
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kMaxWarps = 8;
 // shared control words
@@ -44,11 +44,7 @@ struct SearchParams {
     uint32_t *counters;
     uint32_t *overflow_list;   // primary pass appends here; fallback pass reads from here
     uint32_t *ghash;           // global visited-hash slabs, one per CTA (kGlobalHash only)
-    uint32_t nq;               // primary / drain: number of queries of this pass; fallback: upper bound (count read from counters)
-    uint32_t q_base;           // first query of this pass (drain pass: the last queries of the batch)
-    uint32_t cnt_work;         // which counter hands out the work of this pass
-    uint32_t pdl;              // bit 0: release the dependent (drain) launch as soon as this CTA runs;
-                               // bit 1: do not retire before the primary grid has (keeps stream order for the fallback pass)
+    uint32_t nq;               // primary: number of queries; fallback: unused (count read from counters)
     uint32_t dim, adj_stride, ep, k, L;
     uint32_t hash_log2, hash_limit;
     uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
@@ -100,11 +96,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
     float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
     uint32_t *hash = kGlobalHash ? p.ghash + (size_t(blockIdx.x) << p.hash_log2)
                                  : reinterpret_cast<uint32_t *>(smem_raw + p.off_hash);
-
-    // programmatic dependent launch: the primary grid is sized to be fully resident, so once each of its CTAs has passed
-    // this point the drain grid may be scheduled - its CTAs then take the SM resources of primary CTAs as those run out
-    // of work, instead of leaving them idle during the tail of the batch
-    if (p.pdl & 1u) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const uint32_t dim = p.dim, n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
@@ -181,7 +172,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
     for (;;) {
         // ---- next query (schedule(dynamic,1)) ---------------------------------------------------
         if (tid == 0) {
-            s_ctrl[kCtlWork] = atomicAdd(&p.counters[p.cnt_work], 1u);
+            s_ctrl[kCtlWork] = atomicAdd(&p.counters[p.fallback ? kCntWork2 : kCntWork], 1u);
             s_ctrl[kCtlNvis] = 0;
             s_ctrl[kCtlHop0 + 0] = 0;  // ncand
             s_ctrl[kCtlHop0 + 1] = 0;  // ndup
@@ -196,7 +187,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         const uint32_t w = s_ctrl[kCtlWork];
         const uint32_t nwork = p.fallback ? min(p.counters[kCntOverflow], p.nq) : p.nq;
         if (w >= nwork) break;
-        const uint32_t qi = p.fallback ? p.overflow_list[w] : w + p.q_base;
+        const uint32_t qi = p.fallback ? p.overflow_list[w] : w;
 
         {   // query -> shared memory; clear the visited set
             const float4 *src = reinterpret_cast<const float4 *>(kBuild ? p.base + (size_t(p.node_lo) + qi) * dim
@@ -420,7 +411,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         }
         __syncthreads();
     }
-    if (p.pdl & 2u) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---- host side: geometry + launch ---------------------------------------------------------------
@@ -458,8 +448,7 @@ static SearchKernel pick_kernel(bool ip, int gather, bool gh, bool build) {
     return ip ? rg_search_kernel<true, 1, false, false> : rg_search_kernel<false, 1, false, false>;
 }
 
-static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g,
-                               int warps_override = 0) {
+static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g) {
     SearchParams &p = g->p;
     memset(&p, 0, sizeof(p));
     p.dim = ix->dim;
@@ -475,12 +464,10 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.stage_rows = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
     g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
-    if (warps_override) g->warps = warps_override;
     const uint32_t W = uint32_t(g->warps);
 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || ix->cfg_hash_space != 1);
     p.fallback = fallback ? 1u : 0u;
-    p.cnt_work = fallback ? kCntWork2 : kCntWork;
     p.l2_hint = uint32_t(ix->cfg_l2_hint);
     p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
     // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
@@ -598,38 +585,17 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
 
-    // Drain pass: with a persistent grid of ~13 two-warp CTAs per SM a 10 000-query batch is only ~5 queries per CTA, and
-    // while the last query of every CTA finishes the SMs run progressively empty (the tail costs ~5 % at 10 000 queries,
-    // profiles/r01_k1_variants_10m.txt: 10 000- vs 100 000-query batches).  The last `n_drain` queries are therefore
-    // given to a second grid of 8-warp CTAs (shorter per-query latency) that is launched programmatically dependent on
-    // the primary: it becomes schedulable once every primary CTA is running, and its CTAs take over SM resources as
-    // primary CTAs retire.  Results are the same whichever pass handles a query (tests run every warp count).
-    const uint64_t cap1 = uint64_t(ix->sm_count) * g1.ctas_per_sm;
-    Geometry g3;
-    uint64_t n_drain = 0;
-    int grid3 = 0;
-    if (!build && ix->cfg_drain > 0 && g1.warps < kMaxWarps && nq >= 3 * cap1) {
-        s = make_geometry(ix, k, L, false, false, &g3, kMaxWarps);
-        if (s == RG_OK && g3.global_hash == g1.global_hash && g3.p.hash_log2 == g1.p.hash_log2) {
-            n_drain = std::min<uint64_t>(nq / 4, cap1 * uint64_t(ix->cfg_drain) / 100);
-            grid3 = int(std::min<uint64_t>(n_drain, uint64_t(ix->sm_count) * g3.ctas_per_sm));
-        }
-        if (grid3 <= 0) n_drain = 0;
-    }
-    const uint64_t nq1 = nq - n_drain;
-
     // scratch: overflow list (one slot per query) and global hash slabs (one per CTA)
     s = ensure((void **)&ix->d_overflow_list, &ix->overflow_cap, nq, sizeof(uint32_t));
     if (s != RG_OK) return s;
-    const int grid1 = int(std::min<uint64_t>(nq1, cap1));
+    const int grid1 = int(std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm));
     const int grid2 = ix->sm_count * g2.ctas_per_sm;  // fallback pass: few, heavy queries
     uint64_t need_hash = uint64_t(grid2) << g2.p.hash_log2;
-    if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1 + grid3) << g1.p.hash_log2);
+    if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1) << g1.p.hash_log2);
     s = ensure((void **)&ix->d_ghash, &ix->ghash_words, need_hash, sizeof(uint32_t));
     if (s != RG_OK) return s;
 
-    for (Geometry *g : {&g1, &g2, &g3}) {
-        if (g == &g3 && !n_drain) continue;
+    for (Geometry *g : {&g1, &g2}) {
         g->p.base = ix->d_base;
         g->p.adj = ix->d_adj;
         g->p.queries = d_queries;
@@ -646,15 +612,6 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
         g->p.exp_cnt = d_exp_cnt;
         g->p.exp_cap = exp_cap;
     }
-    g1.p.nq = uint32_t(nq1);
-    if (n_drain) {
-        g1.p.pdl = 1u;
-        g3.p.pdl = 2u;
-        g3.p.nq = uint32_t(n_drain);
-        g3.p.q_base = uint32_t(nq1);
-        g3.p.cnt_work = kCntWork3;
-        g3.p.ghash = ix->d_ghash + (size_t(grid1) << g1.p.hash_log2);  // its slabs follow the primary's
-    }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
     const uint64_t slab_bytes = (uint64_t(grid1) << g1.p.hash_log2) * sizeof(uint32_t);
     if (g1.global_hash && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
@@ -666,22 +623,6 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     }
     RG_CUDA_OK(cudaGetLastError());
     ix->launches++;
-    if (n_drain) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(unsigned(grid3));
-        cfg.blockDim = dim3(unsigned(g3.warps * 32));
-        cfg.dynamicSmemBytes = g3.smem_bytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr;
-        memset(&attr, 0, sizeof(attr));
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        RG_CUDA_OK(cudaLaunchKernelEx(&cfg, g3.fn, g3.p));
-        ix->launches++;
-    }
     g2.fn<<<grid2, g2.warps * 32, g2.smem_bytes, st>>>(g2.p);  // exits immediately when nothing overflowed
     RG_CUDA_OK(cudaGetLastError());
     ix->launches++;

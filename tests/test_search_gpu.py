@@ -198,30 +198,3 @@ def test_pinned_host_buffers_zero_copy(capi):
     with pytest.raises(capi.RoarGraphError):
         ix.set_option("zero_copy", 2)
     ix.close()
-
-
-def test_drain_pass(capi, oracle):
-    """Large batches hand their last queries to a second grid of 8-warp CTAs launched programmatically dependent on the
-    primary (rg_search_set_option "drain").  One resident CTA per SM makes a 2000-query batch "large"; results must not
-    depend on which pass handled a query."""
-    rng = np.random.default_rng(11)
-    n, dim, nq = 20000, 200, 2000
-    base = rng.standard_normal((n, dim)).astype(np.float32)
-    deg = rng.integers(4, 40, n)
-    off = np.zeros(n + 1, np.uint64)
-    np.cumsum(deg, out=off[1:])
-    adj = rng.integers(0, n, int(off[-1])).astype(np.uint32)
-    q = rng.standard_normal((nq, dim)).astype(np.float32)
-    ix = capi.Index(base, off, adj, 5, metric=1)
-    for L in (16, 64):
-        want = oracle.search(base, off, adj, 5, q, 10, L, metric=1)
-        for drain, ctas in ((60, 1), (200, 1), (100, 2), (0, 1)):
-            ix.configure(ctas_per_sm=ctas)
-            ix.set_option("drain", drain)
-            n0 = ix.launches
-            got = ix.search(q, 10, L)
-            report(f"drain={drain} ctas={ctas} L={L}", got, want)
-            assert ix.launches - n0 == (3 if drain else 2), "drain pass launched iff enabled"
-    with pytest.raises(capi.RoarGraphError):
-        ix.set_option("drain", 500)
-    ix.close()
