@@ -382,7 +382,7 @@ def run_ours(args):
                          "kernel": "rg_search_kernel", "algorithmic_bytes_per_launch": int(alg_bytes)},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only; --impl reference times it at every N
             out["cpu_baseline"] = cpu_baseline(args, d, L_sel)
         print(json.dumps(out), flush=True)
     if world > 1:

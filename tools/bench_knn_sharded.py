@@ -3,7 +3,7 @@ the per-shard lists, K4 merge (mysteryann_b200/sharded_knn.py).  Checks the merg
 single-GPU run of the same kernels on the whole base (when it fits) and prints one JSON line (rank 0).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/bench_knn_sharded.py --n 10000000 --nq 262144
+        tools/bench_knn_sharded.py --rows 10000000 --queries 262144
 """
 import argparse
 import json
@@ -20,8 +20,8 @@ from mysteryann_b200 import build, capi, sharded_knn, synth  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=10_000_000)
-    ap.add_argument("--nq", type=int, default=262_144)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=10_000_000)  # under torchrun use --rows (--n is an ambiguous prefix of its own options)
+    ap.add_argument("--nq", "--queries", dest="nq", type=int, default=262_144)
     ap.add_argument("--dim", type=int, default=200)
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--check", type=int, default=4096, help="queries verified against the unsharded answer (0 = none)")

@@ -9,6 +9,6 @@ nvidia-smi --query-gpu=index,name --format=csv > $O/host_${N}gpu.txt; nvidia-smi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 ( time timeout 1200 $TR --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 ) > $O/bench_${N}gpu.txt 2>&1; echo "bench exit $?"; grep '^{' $O/bench_${N}gpu.txt | tail -c 2500
 ( time timeout 900 $TR --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 ) > $O/bench_ref_${N}gpu.txt 2>&1; echo "ref exit $?"; grep '^{' $O/bench_ref_${N}gpu.txt | tail -c 600
-( time timeout 600 $TR --master-port 29513 tools/bench_knn_sharded.py --n 10000000 --nq 262144 ) > $O/knn_sharded_${N}gpu.txt 2>&1; echo "knn exit $?"; grep '^{' $O/knn_sharded_${N}gpu.txt
+( time timeout 600 $TR --master-port 29513 tools/bench_knn_sharded.py --rows 10000000 --queries 262144 ) > $O/knn_sharded_${N}gpu.txt 2>&1; echo "knn exit $?"; grep '^{' $O/knn_sharded_${N}gpu.txt
 ( time timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline ) > $O/bench_1gpu_samebox.txt 2>&1; grep '^{' $O/bench_1gpu_samebox.txt | tail -c 900
 tail -5 $O/bench_${N}gpu.txt
