@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--dim", type=int, default=200)
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--check", type=int, default=4096, help="queries verified against the unsharded answer (0 = none)")
+    ap.add_argument("--warm", type=int, default=65536, help="queries of the untimed warm-up call (NCCL channels, scratch allocation)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -39,10 +40,10 @@ def main():
     shard = base[b[rank]:b[rank + 1]]
     st = torch.cuda.current_stream().cuda_stream
 
-    def run():
-        return sharded_knn.knn_sharded(shard, b[rank], train, a.K, metric=capi.METRIC_IP, gather=False, stream=st)
+    def run(q=train):
+        return sharded_knn.knn_sharded(shard, b[rank], q, a.K, metric=capi.METRIC_IP, gather=False, stream=st)
 
-    run()  # warm-up (NCCL channels, scratch)
+    run(train[:min(a.warm, a.nq)].contiguous())  # warm-up (NCCL channels, scratch)
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
