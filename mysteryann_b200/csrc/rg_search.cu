@@ -535,17 +535,18 @@ static bool persisting_window_fits(const rg_index *ix, uint64_t bytes) {
 }
 
 static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
-                                               cudaStream_t st) {
+                                               cudaStream_t st, float hit_ratio = 1.0f, uint64_t set_aside = 0) {
     {   // device-wide limit shared by every index on the device
         static std::mutex mu;
         static uint64_t current[64] = {0};
         std::lock_guard<std::mutex> lock(mu);
         uint64_t &cur = current[ix->device & 63];
-        if (cur != bytes) {
-            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(bytes)));
-            cur = bytes;
+        const uint64_t want = set_aside ? set_aside : bytes;
+        if (cur != want) {
+            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(want)));
+            cur = want;
         }
-        ix->persist_bytes = bytes;
+        ix->persist_bytes = want;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -558,7 +559,7 @@ static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, 
     attr.id = cudaLaunchAttributeAccessPolicyWindow;
     attr.val.accessPolicyWindow.base_ptr = ptr;
     attr.val.accessPolicyWindow.num_bytes = size_t(bytes);
-    attr.val.accessPolicyWindow.hitRatio = 1.0f;
+    attr.val.accessPolicyWindow.hitRatio = hit_ratio;
     attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     cfg.attrs = &attr;
@@ -617,6 +618,16 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     if (g1.global_hash && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
         s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, st);
+        if (s != RG_OK) return s;
+    } else if (g1.global_hash && (ix->cfg_l2_hint & 2) && !build && getenv("RG_SEARCH_PERSIST_PARTIAL")) {
+        // experiment: slabs larger than the set-aside - pin a fraction of the window's lines
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
+        const uint64_t win = std::min<uint64_t>(slab_bytes, uint64_t(max_window));
+        const double share = atof(getenv("RG_SEARCH_PERSIST_PARTIAL"));  // share of the set-aside to use
+        const uint64_t aside = uint64_t(double(max_persist) * share);
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, win, st, float(std::min(1.0, double(aside) / double(win))), aside);
         if (s != RG_OK) return s;
     } else {
         g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
