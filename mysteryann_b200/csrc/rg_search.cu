@@ -448,7 +448,8 @@ static SearchKernel pick_kernel(bool ip, int gather, bool gh, bool build) {
     return ip ? rg_search_kernel<true, 1, false, false> : rg_search_kernel<false, 1, false, false>;
 }
 
-static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g) {
+static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g,
+                               int warps_override = 0) {
     SearchParams &p = g->p;
     memset(&p, 0, sizeof(p));
     p.dim = ix->dim;
@@ -464,6 +465,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.stage_rows = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
     g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
+    if (warps_override) g->warps = warps_override;
     const uint32_t W = uint32_t(g->warps);
 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || ix->cfg_hash_space != 1);
@@ -535,18 +537,17 @@ static bool persisting_window_fits(const rg_index *ix, uint64_t bytes) {
 }
 
 static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
-                                               cudaStream_t st, float hit_ratio = 1.0f, uint64_t set_aside = 0) {
+                                               cudaStream_t st) {
     {   // device-wide limit shared by every index on the device
         static std::mutex mu;
         static uint64_t current[64] = {0};
         std::lock_guard<std::mutex> lock(mu);
         uint64_t &cur = current[ix->device & 63];
-        const uint64_t want = set_aside ? set_aside : bytes;
-        if (cur != want) {
-            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(want)));
-            cur = want;
+        if (cur != bytes) {
+            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(bytes)));
+            cur = bytes;
         }
-        ix->persist_bytes = want;
+        ix->persist_bytes = bytes;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -559,7 +560,7 @@ static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, 
     attr.id = cudaLaunchAttributeAccessPolicyWindow;
     attr.val.accessPolicyWindow.base_ptr = ptr;
     attr.val.accessPolicyWindow.num_bytes = size_t(bytes);
-    attr.val.accessPolicyWindow.hitRatio = hit_ratio;
+    attr.val.accessPolicyWindow.hitRatio = 1.0f;
     attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     cfg.attrs = &attr;
@@ -585,6 +586,21 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     if (s != RG_OK) return s;
     s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
+
+    // Warps per query, automatic mode: two warps per query keep the most queries resident, but from L_pq ~ 80 on their
+    // visited-hash slabs (64 KB each) no longer fit the persisting part of L2 together and the probes go to HBM.  Four
+    // warps per query halve the resident queries, so up to L_pq ~ 180 the slabs fit again: 0.74 -> 0.81 of the HBM peak
+    // at L_pq = 100 (profiles/r01_k1_large_L_variants.txt).  Beyond that nothing fits and two warps win again.
+    if (!build && ix->cfg_warps == 0 && g1.global_hash && (ix->cfg_l2_hint & 2)) {
+        const uint64_t cap2 = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm);
+        if (!persisting_window_fits(ix, (cap2 << g1.p.hash_log2) * sizeof(uint32_t))) {
+            Geometry g4;
+            if (make_geometry(ix, k, L, false, false, &g4, 4) == RG_OK && g4.global_hash) {
+                const uint64_t cap4 = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g4.ctas_per_sm);
+                if (persisting_window_fits(ix, (cap4 << g4.p.hash_log2) * sizeof(uint32_t))) g1 = g4;
+            }
+        }
+    }
 
     // scratch: overflow list (one slot per query) and global hash slabs (one per CTA)
     s = ensure((void **)&ix->d_overflow_list, &ix->overflow_cap, nq, sizeof(uint32_t));
@@ -618,16 +634,6 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     if (g1.global_hash && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
         s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, st);
-        if (s != RG_OK) return s;
-    } else if (g1.global_hash && (ix->cfg_l2_hint & 2) && !build && getenv("RG_SEARCH_PERSIST_PARTIAL")) {
-        // experiment: slabs larger than the set-aside - pin a fraction of the window's lines
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
-        const uint64_t win = std::min<uint64_t>(slab_bytes, uint64_t(max_window));
-        const double share = atof(getenv("RG_SEARCH_PERSIST_PARTIAL"));  // share of the set-aside to use
-        const uint64_t aside = uint64_t(double(max_persist) * share);
-        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, win, st, float(std::min(1.0, double(aside) / double(win))), aside);
         if (s != RG_OK) return s;
     } else {
         g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);

@@ -198,3 +198,19 @@ def test_pinned_host_buffers_zero_copy(capi):
     with pytest.raises(capi.RoarGraphError):
         ix.set_option("zero_copy", 2)
     ix.close()
+
+
+def test_auto_warps_rule_large_batch(capi, oracle):
+    """With enough queries to fill the GPU and L_pq in ~[80, 180] the library switches to four warps per query so that the
+    visited-hash slabs of the resident CTAs fit the persisting part of L2 (rg_search.cu, search_device_impl); the
+    results must not change.  3000 queries at L_pq = 100 take that branch on a B200, L_pq = 40 and 300 do not."""
+    rng = np.random.default_rng(21)
+    n, dim, nq = 30000, 200, 3000
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 8, 40)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = capi.Index(base, off, adj, 7, metric=1)
+    for L in (100, 40, 300):
+        want = oracle.search(base, off, adj, 7, q, 10, L, metric=1)
+        report(f"auto warps L={L}", ix.search(q, 10, L), want)
+    ix.close()
