@@ -291,6 +291,47 @@ __device__ __forceinline__ uint32_t take_hits(const MaxTree &t, const uint32_t (
     bulk_append<kL2>(v, bn, half_scale, theta, inv_scale, row_first, n_valid, n_hits, count, my_cand);
     return n_st;
 }
+// Sparse blocks (everything after the first few): no hit counting at all - a warp gets here when ANY of its lanes has a
+// hit (~1 lane in 100), and the exact 32-column count of the dense path would then cost the whole warp several times the
+// max tree (measured: 512K-row block 5.35 ms -> 6.66 ms).  Hits are staged while there is room; the rare extra hit takes
+// one returning atomic.
+__device__ __noinline__ void direct_append(uint32_t *count, uint64_t *my_cand, uint64_t key) {
+    const uint32_t pos = atomicAdd(count, 1u);
+    if (pos < kCap) my_cand[pos] = key;
+}
+template <bool kL2>
+__device__ __forceinline__ uint32_t take_hits_sparse(const MaxTree &t, const uint32_t (&v)[32], const float *bn, float half_scale,
+                                                     float theta, float inv_scale, uint64_t row_first, uint64_t n_valid,
+                                                     uint64_t *st, uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (t.b[g] > theta) {
+#pragma unroll
+            for (int tt = 3 * g; tt < 3 * g + 3 && tt < 11; ++tt) {
+                if (t.a[tt] > theta) {
+#pragma unroll
+                    for (int i = 3 * tt; i < 3 * tt + 3 && i < 32; ++i) {
+                        if (filt<kL2>(v[i], bn, i, half_scale) > theta) {
+                            const uint64_t row = row_first + i;
+                            const float a = __uint_as_float(v[i]);
+                            const float sc = kL2 ? fmaf(-2.f * inv_scale, a, bn[i]) : -(a * inv_scale);
+                            if (row < n_valid) {
+                                const uint64_t key = (uint64_t(float_to_ordered(sc)) << 32) | uint32_t(row);
+                                if (n_st < kStageSlots) {
+                                    st[n_st * 32] = key;
+                                    ++n_st;
+                                } else {
+                                    direct_append(count, my_cand, key);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return n_st;
+}
 // one reservation per lane for everything it staged, then the copies
 __device__ __noinline__ void stage_flush(const uint64_t *st, uint32_t n_st, uint32_t *count, uint64_t *my_cand) {
     if (n_st) {
@@ -300,7 +341,9 @@ __device__ __noinline__ void stage_flush(const uint64_t *st, uint32_t n_st, uint
     }
 }
 
-template <bool kL2>
+// kDense: the epilogue may meet many hits per accumulator slice (the first blocks of a query batch, where the threshold is
+// still loose) and reserves list room in bulk; otherwise hits are rare and are staged one by one.
+template <bool kL2, bool kDense>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                        const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bt,
@@ -494,12 +537,16 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     MaxTree t;
                     build_tree<kL2>(v0, bn, half_scale, t);
                     if (t.m > theta)  // rare per lane: a few candidates per query per block
-                        n_st = take_hits<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st, n_st,
-                                              p.cand_count + q, my_cand);
+                        n_st = kDense ? take_hits<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st, n_st,
+                                                       p.cand_count + q, my_cand)
+                                      : take_hits_sparse<kL2>(t, v0, bn, half_scale, theta, p.inv_scale, row0 + c0, p.n_valid, st,
+                                                              n_st, p.cand_count + q, my_cand);
                     build_tree<kL2>(v1, bn + 32, half_scale, t);
                     if (t.m > theta)
-                        n_st = take_hits<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32, p.n_valid, st, n_st,
-                                              p.cand_count + q, my_cand);
+                        n_st = kDense ? take_hits<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32, p.n_valid, st,
+                                                       n_st, p.cand_count + q, my_cand)
+                                      : take_hits_sparse<kL2>(t, v1, bn + 32, half_scale, theta, p.inv_scale, row0 + c0 + 32,
+                                                              p.n_valid, st, n_st, p.cand_count + q, my_cand);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -995,8 +1042,10 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     n_stages = std::min<uint32_t>(n_stages, 16);
     const size_t gemm_smem = size_t(a_bufs) * a_bytes + size_t(n_stages) * kSlabBytes + misc;
     (void)nslab;
-    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
-    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
+    RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
     // persistent grid: as many CTA pairs as the device can co-schedule (one CTA per SM, pairs on one TPC); the
     // occupancy query costs tens of milliseconds, so its answer is cached per (device, shared-memory size)
     uint32_t max_pairs = uint32_t(sms) / 2;
@@ -1025,7 +1074,7 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
             int active = 0;
-            if (cudaOccupancyMaxActiveClusters(&active, knn_gemm_filter_kernel<false>, &cfg) == cudaSuccess && active > 0)
+            if (cudaOccupancyMaxActiveClusters(&active, knn_gemm_filter_kernel<false, true>, &cfg) == cudaSuccess && active > 0)
                 max_pairs = std::min<uint32_t>(max_pairs, uint32_t(active));
             else
                 (void)cudaGetLastError();
@@ -1076,6 +1125,12 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             const long g = e ? atol(e) : 2;
             return uint64_t(g < 2 ? 2 : (g > 8 ? 8 : g));
         }();
+        // RG_KNN_DENSE_ROWS: blocks that start before this many rows use the dense-hit epilogue (default 4096 = the first
+        // three blocks; measured per block at 10M x 32768, profiles/r01_launches_knn_*)
+        static const uint64_t dense_rows = [] {
+            const char *e = getenv("RG_KNN_DENSE_ROWS");
+            return uint64_t(e ? atoll(e) : 4096);
+        }();
         uint64_t lo = 0, len = kCap;
         while (lo < b_rows_pad) {
             const uint64_t hi = std::min(b_rows_pad, lo + len);
@@ -1083,8 +1138,15 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             gp.n_tiles = uint32_t((hi - lo) / kPairN);
             const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
             const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
-            if (ip) knn_gemm_filter_kernel<false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-            else knn_gemm_filter_kernel<true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+            // the threshold after `lo` rows lets ~k' / lo of the scores through: dense handling only while that is percents
+            const bool dense = lo < dense_rows;
+            if (ip) {
+                if (dense) knn_gemm_filter_kernel<false, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                else knn_gemm_filter_kernel<false, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+            } else {
+                if (dense) knn_gemm_filter_kernel<true, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                else knn_gemm_filter_kernel<true, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+            }
             knn_select_kernel<<<(bq + 3) / 4, 128, 0, st>>>(cand, cand_count, thr, overflow, bq, kprime);
             launches += 2;
             lo = hi;
