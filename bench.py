@@ -233,7 +233,9 @@ def load_traffic(args, L):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
         w = t["workload"]
-        if (w["n_base"], w["dim"], w["queries"], w["L_pq"], w["k"]) == (args.n, args.dim, args.queries, L, args.k):
+        n_train = args.train or max(50_000, args.n // 5)
+        if (w["n_base"], w["dim"], w["queries"], w["L_pq"], w["k"], w.get("n_train", n_train)) == \
+                (args.n, args.dim, args.queries, L, args.k, n_train):
             return int(t["dram_bytes_per_launch"])
     except Exception:
         pass

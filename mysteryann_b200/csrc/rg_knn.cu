@@ -120,6 +120,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// The wait that makes the registers of outstanding tcgen05.ld's valid, tied to those registers: the "+r" operands make
+// every later use of v depend on this statement, so the compiler cannot hoist pure arithmetic on the loaded values above
+// the wait (a volatile asm with a memory clobber alone only orders memory operations and other volatile asms).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 
 // Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major, swizzled: low word = start address >> 4,
 // high word = SBO (8 rows x row bytes) >> 4 | version 1 << 14 | layout << 29 (2 = 128B swizzle: 64 halves per row,
@@ -528,7 +540,8 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     uint32_t v0[32], v1[32];
                     tmem_ld32_nowait(taddr, v0);
                     tmem_ld32_nowait(taddr + 32, v1);
-                    tmem_ld_wait();
+                    tmem_ld_wait(v0);  // one hardware wait covers both loads; the second statement only adds the
+                    tmem_ld_wait(v1);  // register dependency for v1 (tcgen05.wait::ld with nothing outstanding is free)
                     // "does any of my accumulators beat the threshold": a 3-input max tree (FMNMX3) over the raw, scaled
                     // values and ONE compare; the slices are only indexed with constants so they stay in registers.
                     //   IP: -<q,b> < tau            <=>  acc > -tau * scale
