@@ -32,12 +32,12 @@ int main(int argc, char **argv) {
     std::string base_data_file, query_file, gt_file, projection_index_save_file, data_type, dist, evaluation_save_path;
     std::vector<uint32_t> L_vec;
     uint32_t num_threads, k;
-    int device;
+    int device, devices;
     try {
         CliArgs args(argc, argv, {{"-T", "--num_threads"}, {"-h", "--help"}});
         if (args.has("help")) {
             std::cout << "Arguments: --data_type <float> --dist <l2/ip/cosine> --base_data_path F --query_path F --gt_path F\n"
-                         "  --projection_index_save_path F --L_pq <L...> --k K [--evaluation_save_path F] [-T threads] [--device D]\n";
+                         "  --projection_index_save_path F --L_pq <L...> --k K [--evaluation_save_path F] [-T threads] [--device D] [--devices N]\n";
             return 0;
         }
         data_type = args.get<std::string>("data_type");
@@ -51,6 +51,7 @@ int main(int argc, char **argv) {
         evaluation_save_path = args.get<std::string>("evaluation_save_path", "");
         num_threads = args.get<uint32_t>("num_threads", (uint32_t)omp_get_num_procs());
         device = args.get<int>("device", 0);
+        devices = args.get<int>("devices", 1);  // replicate the index on N GPUs and shard the queries
     } catch (const std::exception &ex) {
         std::cerr << ex.what() << '\n';
         return -1;
@@ -89,6 +90,7 @@ int main(int argc, char **argv) {
     }
     efanna2e::IndexBipartite index(q_dim, base_num, dist_metric, nullptr);
     index.SetDevice(device);
+    index.SetDeviceCount(devices);
     index.LoadSearchNeededData(base_data_file.c_str(), "");
     std::cout << "Load graph index: " << projection_index_save_file << std::endl;
     index.LoadProjectionGraph(projection_index_save_file.c_str());
@@ -112,7 +114,7 @@ int main(int argc, char **argv) {
             std::cout << "note: buffer not page-locked (" << rg_last_error_string() << "), results are staged" << std::endl;
     std::ofstream evaluation_out;
     if (!evaluation_save_path.empty()) evaluation_out.open(evaluation_save_path, std::ios::out);
-    std::cout << "Using GPU device: " << device << std::endl;
+    std::cout << "Using GPU device: " << device << (devices > 1 ? " .. " + std::to_string(device + devices - 1) + " (index replicated, queries sharded)" : std::string()) << std::endl;
     std::cout << "L_pq" << "\t\tQPS" << "\t\t\tavg_visited" << "\tmean_latency" << "\trecall@" << k << "\tavg_hops" << std::endl;
     for (uint32_t L_pq : L_vec) {
         if (k > L_pq) {

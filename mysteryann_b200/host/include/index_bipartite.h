@@ -57,6 +57,10 @@ class IndexBipartite : public Index {
     void SetProjectionGraph(uint32_t ep, CompactGraph graph);  // adopt an externally built graph
     void SetBaseData(const float *base, size_t n);             // adopt caller-owned padded rows
     void SetDevice(int device) { device_ = device; }
+    // Search on `count` GPUs (devices device_ .. device_ + count - 1): the index is replicated on each of them and every
+    // SearchRoarGraphBatch call splits its queries into `count` contiguous slices, one host thread per GPU - the
+    // query sharding the reference does with OpenMP threads (tests/test_search_roargraph.cpp:203).  No collective.
+    void SetDeviceCount(int count) { device_count_ = count < 1 ? 1 : count; }
 
     bool need_normalize = false;  // index_bipartite.h:145 (COSINE)
 
@@ -73,8 +77,9 @@ class IndexBipartite : public Index {
     std::vector<std::mutex> locks_;
     uint32_t projection_ep_ = 0;
     float *owned_base_ = nullptr;  // allocated by LoadVectorData, never freed by the reference either
-    rg_index *device_index_ = nullptr;
-    int device_ = 0;
+    rg_index *device_index_ = nullptr;          // replica on device_
+    std::vector<rg_index *> extra_replicas_;    // replicas on device_ + 1 .. device_ + device_count_ - 1
+    int device_ = 0, device_count_ = 1;
     std::mutex device_mutex_;
 };
 

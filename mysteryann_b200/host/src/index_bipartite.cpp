@@ -16,6 +16,9 @@
 #include <limits>
 #include <sstream>
 #include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../../include/roargraph_b200.h"
 
@@ -144,6 +147,8 @@ void IndexBipartite::release_device() {
         rg_index_destroy(device_index_);
         device_index_ = nullptr;
     }
+    for (rg_index *r : extra_replicas_) rg_index_destroy(r);
+    extra_replicas_.clear();
 }
 
 void IndexBipartite::upload_to_device() {
@@ -156,9 +161,27 @@ void IndexBipartite::upload_to_device() {
     for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + projection_graph_[i].size();
     std::vector<uint32_t> adj(offsets[n]);
     for (size_t i = 0; i < n; ++i) std::copy(projection_graph_[i].begin(), projection_graph_[i].end(), adj.begin() + offsets[i]);
-    if (rg_index_create(&device_index_, data_bp_, n, (uint32_t)dimension_, rg_metric(metric_), offsets.data(),
-                        adj.data(), projection_ep_, device_, 0) != RG_OK)
-        throw_rg("rg_index_create");
+    if (device_ + device_count_ > rg_device_count() && rg_device_count() > 0)
+        throw std::runtime_error("SetDeviceCount: only " + std::to_string(rg_device_count()) + " CUDA device(s) visible");
+    // one replica per GPU, uploaded concurrently (the host arrays are read-only here)
+    std::vector<rg_index *> replicas(device_count_, nullptr);
+    std::vector<std::string> errors(device_count_);
+    auto upload = [&](int r) {
+        if (rg_index_create(&replicas[r], data_bp_, n, (uint32_t)dimension_, rg_metric(metric_), offsets.data(), adj.data(),
+                            projection_ep_, device_ + r, 0) != RG_OK)
+            errors[r] = rg_last_error_string();
+    };
+    std::vector<std::thread> threads;
+    for (int r = 1; r < device_count_; ++r) threads.emplace_back(upload, r);
+    upload(0);
+    for (auto &t : threads) t.join();
+    for (int r = 0; r < device_count_; ++r)
+        if (!replicas[r]) {
+            for (rg_index *x : replicas) rg_index_destroy(x);
+            throw std::runtime_error("rg_index_create: " + errors[r]);
+        }
+    device_index_ = replicas[0];
+    extra_replicas_.assign(replicas.begin() + 1, replicas.end());
 }
 
 void IndexBipartite::InitVisitedListPool(uint32_t) { upload_to_device(); }  // index_bipartite.h:133
@@ -167,9 +190,31 @@ void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_
                                           unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
     const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");  // :2313
     if (!device_index_) upload_to_device();
-    const rg_status s = rg_search_batch(device_index_, queries, nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);
-    if (s == RG_ERR_NOT_ENOUGH_RESULTS) throw std::runtime_error(rg_last_error_string());  // :2408-2412
-    if (s != RG_OK) throw_rg("rg_search_batch");
+    const size_t G = 1 + extra_replicas_.size();
+    if (G == 1 || nq < G) {
+        const rg_status s = rg_search_batch(device_index_, queries, nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);
+        if (s == RG_ERR_NOT_ENOUGH_RESULTS) throw std::runtime_error(rg_last_error_string());  // :2408-2412
+        if (s != RG_OK) throw_rg("rg_search_batch");
+        return;
+    }
+    // contiguous query slices, one host thread per replica; results land in disjoint slices of the caller's arrays
+    std::vector<rg_status> status(G, RG_OK);
+    std::vector<std::string> errors(G);
+    auto run = [&](size_t r) {
+        const size_t lo = nq * r / G, hi = nq * (r + 1) / G;
+        rg_index *ix = r == 0 ? device_index_ : extra_replicas_[r - 1];
+        status[r] = rg_search_batch(ix, queries + lo * dimension_, hi - lo, (uint32_t)k, L_pq, indices + lo * k, dists + lo * k,
+                                    cmps ? cmps + lo : nullptr, hops ? hops + lo : nullptr);
+        if (status[r] != RG_OK) errors[r] = rg_last_error_string();  // the message is thread-local
+    };
+    std::vector<std::thread> threads;
+    for (size_t r = 1; r < G; ++r) threads.emplace_back(run, r);
+    run(0);
+    for (auto &t : threads) t.join();
+    for (size_t r = 0; r < G; ++r) {
+        if (status[r] == RG_ERR_NOT_ENOUGH_RESULTS) throw std::runtime_error(errors[r]);  // :2408-2412
+        if (status[r] != RG_OK) throw std::runtime_error("rg_search_batch: " + errors[r]);
+    }
 }
 
 std::pair<uint32_t, uint32_t> IndexBipartite::SearchRoarGraph(const float *query, size_t k, size_t &,

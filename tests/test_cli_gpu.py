@@ -117,3 +117,32 @@ def test_pipeline_knn_build_search(bins, oracle, tmp_path):
         assert abs(float(r[2]) - want["cmps"].mean()) < 1e-2 * max(1.0, want["cmps"].mean() * 1e-3), (L, r)
         assert abs(float(r[5]) - want["hops"].mean()) < 1e-2, (L, r)
     assert float(rows[-1][4]) > 0.9   # the GPU-built graph is a working RoarGraph
+
+
+def test_search_driver_multi_gpu_flag(bins, oracle, tmp_path):
+    """--devices N replicates the index on N GPUs and shards the queries over one host thread per GPU: the CSV (recall,
+    avg cmps, avg hops) must equal the single-GPU run's; asking for more GPUs than are visible is an error."""
+    from mysteryann_b200 import capi, hostlib, io, synth
+
+    base, train, test = synth.make_numpy(6000, 6000, 301, 200, seed=5)
+    knn, _, _ = oracle.exact_knn(base, train, 100, metric=1)
+    for name, x in (("base.fbin", base), ("test.fbin", test)):
+        io.write_fbin(tmp_path / name, x)
+    hostlib.build_index(base, train, knn, str(tmp_path / "rg.index"), metric=1, M_sq=100, M_pjbp=35, L_pjpq=100, threads=4)
+    gt, gd, _ = oracle.exact_knn(base, test, 100, metric=1)
+    io.write_ibin(tmp_path / "gt.bin", gt, gd)
+    cmd = [os.path.join(bins, "test_search_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path",
+           str(tmp_path / "base.fbin"), "--query_path", str(tmp_path / "test.fbin"), "--gt_path", str(tmp_path / "gt.bin"),
+           "--projection_index_save_path", str(tmp_path / "rg.index"), "--k", "10", "--L_pq", "10", "40", "100"]
+
+    def rows(path):
+        return [[float(v) for i, v in enumerate(line.strip().split(",")) if i in (0, 2, 4, 5)] for line in open(path) if line.strip()]
+
+    run(cmd + ["--evaluation_save_path", str(tmp_path / "one.csv")])
+    n_dev = capi.device_count()
+    if n_dev >= 2:
+        out = run(cmd + ["--evaluation_save_path", str(tmp_path / "two.csv"), "--devices", "2"])
+        assert "queries sharded" in out
+        assert rows(tmp_path / "one.csv") == rows(tmp_path / "two.csv")
+    p = subprocess.run(cmd + ["--devices", str(n_dev + 1)], capture_output=True, text=True, timeout=600)
+    assert p.returncode != 0 and "CUDA device(s) visible" in (p.stdout + p.stderr)
