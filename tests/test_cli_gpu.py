@@ -146,3 +146,52 @@ def test_search_driver_multi_gpu_flag(bins, oracle, tmp_path):
         assert rows(tmp_path / "one.csv") == rows(tmp_path / "two.csv")
     p = subprocess.run(cmd + ["--devices", str(n_dev + 1)], capture_output=True, text=True, timeout=600)
     assert p.returncode != 0 and "CUDA device(s) visible" in (p.stdout + p.stderr)
+
+
+def test_search_driver_l2_and_cosine(bins, oracle, tmp_path):
+    """test_search_roargraph with --dist l2 (CSV must equal the oracle's numbers on the same index file) and --dist cosine
+    (the driver normalises base rows and queries like the reference, src/index_bipartite.cpp:2675-2680 and
+    tests/test_search_roargraph.cpp:167-172, then searches with the inner product: it must agree with an inner-product
+    search over rows normalised beforehand, up to the rounding of the two normalisations)."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(17)
+    n, dim, nq = 3000, 200, 200
+    base = (rng.standard_normal((n, dim)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    test = (rng.standard_normal((nq, dim)) + 0.3).astype(np.float32)
+    deg = rng.integers(8, 25, n)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=off[1:])
+    adj = rng.integers(0, n, int(off[-1])).astype(np.uint32)
+    ep = 11
+    io.write_fbin(tmp_path / "base.fbin", base)
+    io.write_fbin(tmp_path / "test.fbin", test)
+    io.write_index(tmp_path / "rnd.index", ep, off, adj)
+    Ls = [10, 30, 60]
+
+    def drive(dist, gt_name, csv_name):
+        run([os.path.join(bins, "test_search_roargraph"), "--data_type", "float", "--dist", dist, "--base_data_path",
+             str(tmp_path / "base.fbin"), "--query_path", str(tmp_path / "test.fbin"), "--gt_path", str(tmp_path / gt_name),
+             "--projection_index_save_path", str(tmp_path / "rnd.index"), "--k", "10", "--evaluation_save_path",
+             str(tmp_path / csv_name), "--L_pq"] + [str(L) for L in Ls])
+        rows = [[float(v) for v in line.strip().split(",")] for line in open(tmp_path / csv_name) if line.strip()]
+        assert [int(r[0]) for r in rows] == Ls
+        return rows
+
+    # L2: exact agreement with the oracle
+    gt, gd, _ = oracle.exact_knn(base, test, 100, metric=0)
+    io.write_ibin(tmp_path / "gt_l2.bin", gt, gd)
+    for r in drive("l2", "gt_l2.bin", "l2.csv"):
+        want = oracle.search(base, off, adj, ep, test, 10, int(r[0]), metric=0)
+        assert abs(r[4] - oracle.recall(want["ids"], gt, 10)) < 1e-5, r
+        assert abs(r[2] - want["cmps"].mean()) < 1e-2 and abs(r[5] - want["hops"].mean()) < 1e-2, r
+
+    # cosine: the same as inner product over pre-normalised rows
+    nb = (base / np.linalg.norm(base, axis=1, keepdims=True)).astype(np.float32)
+    nt = (test / np.linalg.norm(test, axis=1, keepdims=True)).astype(np.float32)
+    gt, gd, _ = oracle.exact_knn(nb, nt, 100, metric=1)
+    io.write_ibin(tmp_path / "gt_cos.bin", gt, gd)
+    for r in drive("cosine", "gt_cos.bin", "cos.csv"):
+        want = oracle.search(nb, off, adj, ep, nt, 10, int(r[0]), metric=1)
+        assert abs(r[4] - oracle.recall(want["ids"], gt, 10)) < 5e-3, r
+        assert abs(r[2] - want["cmps"].mean()) < 5e-3 * want["cmps"].mean() and abs(r[5] - want["hops"].mean()) < 0.5, r
