@@ -81,6 +81,7 @@ class IndexBipartite : public Index {
     std::vector<rg_index *> extra_replicas_;    // replicas on device_ + 1 .. device_ + device_count_ - 1
     int device_ = 0, device_count_ = 1;
     std::mutex device_mutex_;
+    std::mutex search_mutex_;  // the GPU replicas own one set of scratch buffers each: concurrent callers take turns
 };
 
 }  // namespace efanna2e

@@ -50,4 +50,48 @@ __attribute__((visibility("default"))) int rgh_build_index(const float *base, ui
         return 1;
     }
 }
+
+// The reference driver's own search loop (tests/test_search_roargraph.cpp:160-209) on files: load base + index, then ONE
+// SearchRoarGraph CALL PER QUERY from num_threads OpenMP threads (schedule(dynamic,1)) - the way existing callers of the
+// reference use the class.  queries: nq padded rows.  Outputs: ids/dists [nq*k], cmps/hops [nq].
+__attribute__((visibility("default"))) int rgh_search_per_query(const char *base_fbin, const char *index_file, int metric,
+                                                                 const float *queries, uint64_t nq, uint32_t k, uint32_t L_pq,
+                                                                 uint32_t num_threads, uint32_t *ids, float *dists,
+                                                                 uint32_t *cmps, uint32_t *hops) {
+    try {
+        Mute mute(true);
+        uint32_t base_num = 0, base_dim = 0;
+        efanna2e::load_meta<float>(base_fbin, base_num, base_dim);
+        const uint32_t dim = (base_dim + 7) / 8 * 8;
+        efanna2e::IndexBipartite index(dim, base_num, static_cast<efanna2e::Metric>(metric), nullptr);
+        index.LoadSearchNeededData(base_fbin, "");
+        index.LoadProjectionGraph(index_file);
+        index.InitVisitedListPool(num_threads);
+        efanna2e::Parameters p;
+        p.Set<uint32_t>("L_pq", L_pq);
+        std::string first_error;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
+        for (int64_t i = 0; i < (int64_t)nq; ++i) {
+            try {
+                size_t qid = (size_t)i;
+                std::vector<float> res_dists(k);
+                auto ch = index.SearchRoarGraph(queries + (size_t)i * dim, k, qid, p, ids + (size_t)i * k, res_dists);
+                std::memcpy(dists + (size_t)i * k, res_dists.data(), k * sizeof(float));
+                cmps[i] = ch.first;
+                hops[i] = ch.second;
+            } catch (const std::exception &ex) {
+#pragma omp critical
+                if (first_error.empty()) first_error = ex.what();
+            }
+        }
+        if (!first_error.empty()) {
+            g_err = first_error;
+            return 1;
+        }
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return 1;
+    }
+}
 }

@@ -190,6 +190,9 @@ void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_
                                           unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
     const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");  // :2313
     if (!device_index_) upload_to_device();
+    // SearchRoarGraph is re-entrant in the reference (called from OpenMP threads, tests/test_search_roargraph.cpp:203);
+    // here every call is a GPU batch on the index's own stream and scratch, so concurrent callers are serialised.
+    std::lock_guard<std::mutex> serial(search_mutex_);
     const size_t G = 1 + extra_replicas_.size();
     if (G == 1 || nq < G) {
         const rg_status s = rg_search_batch(device_index_, queries, nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);

@@ -28,6 +28,9 @@ def lib():
         _lib.rgh_build_index.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                          C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_char_p, C.c_int, C.c_void_p]
+        _lib.rgh_search_per_query.restype = C.c_int
+        _lib.rgh_search_per_query.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                              C.c_uint32] + [C.c_void_p] * 4
     return _lib
 
 
@@ -44,3 +47,20 @@ def build_index(base, train, knn_ids, out_path, metric=1, M_sq=100, M_pjbp=35, L
     if rc:
         raise RuntimeError(lib().rgh_last_error().decode())
     return sec.value
+
+
+def search_per_query(base_fbin, index_file, queries, k, L_pq, metric=1, threads=8):
+    """The reference driver's loop on the drop-in class: one IndexBipartite::SearchRoarGraph call per query from `threads`
+    OpenMP threads (each call is a GPU batch of one).  Returns dict(ids, dists, cmps, hops)."""
+    queries = np.ascontiguousarray(queries, np.float32)
+    nq = queries.shape[0]
+    assert queries.shape[1] % 8 == 0
+    ids = np.empty((nq, k), np.uint32)
+    dists = np.empty((nq, k), np.float32)
+    cmps = np.empty(nq, np.uint32)
+    hops = np.empty(nq, np.uint32)
+    rc = lib().rgh_search_per_query(str(base_fbin).encode(), str(index_file).encode(), metric, queries.ctypes.data, nq, k,
+                                    L_pq, threads, ids.ctypes.data, dists.ctypes.data, cmps.ctypes.data, hops.ctypes.data)
+    if rc:
+        raise RuntimeError(lib().rgh_last_error().decode())
+    return dict(ids=ids, dists=dists, cmps=cmps, hops=hops)

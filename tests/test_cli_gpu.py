@@ -195,3 +195,21 @@ def test_search_driver_l2_and_cosine(bins, oracle, tmp_path):
         want = oracle.search(nb, off, adj, ep, nt, 10, int(r[0]), metric=1)
         assert abs(r[4] - oracle.recall(want["ids"], gt, 10)) < 5e-3, r
         assert abs(r[2] - want["cmps"].mean()) < 5e-3 * want["cmps"].mean() and abs(r[5] - want["hops"].mean()) < 0.5, r
+
+
+def test_per_query_api_from_openmp_threads(tmp_path):
+    """Existing callers of the reference call IndexBipartite::SearchRoarGraph once per query from OpenMP threads
+    (tests/test_search_roargraph.cpp:203-209).  The drop-in class must give the reference's answers that way too
+    (each call is a GPU batch of one; concurrent callers are serialised inside the class)."""
+    from conftest import load_case
+    from mysteryann_b200 import hostlib, io
+
+    hostlib.build()
+    c = load_case("ip_d200")
+    io.write_fbin(tmp_path / "base.fbin", c["base"])
+    io.write_index(tmp_path / "g.index", c["ep"], c["offsets"], c["adj"])
+    for L in (10, 32):
+        got = hostlib.search_per_query(tmp_path / "base.fbin", tmp_path / "g.index", c["test"], 10, L, metric=1, threads=8)
+        for key in ("ids", "cmps", "hops"):
+            assert (got[key] == c[f"{key}_{L}"]).all(), (key, L)
+        assert (got["dists"].view(np.uint32) == c[f"dists_{L}"].view(np.uint32)).all()

@@ -81,3 +81,17 @@ def test_cli_flags(tmp_path):
     assert (np.fromfile(p("out.index"), dtype=np.uint8) == c["index"]).all()
     r = subprocess.run([exe, "--dist", "ip"], capture_output=True, text=True)   # missing required flags
     assert r.returncode != 0 and "required" in r.stderr
+
+
+def test_search_without_gpu_fails_loudly(tmp_path):
+    """The host class has no CPU search path: without a CUDA device InitVisitedListPool / SearchRoarGraph raise."""
+    from conftest import load_case
+    from mysteryann_b200 import capi, hostlib, io
+
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    c = load_case("ip_d200")
+    io.write_fbin(tmp_path / "base.fbin", c["base"])
+    io.write_index(tmp_path / "g.index", c["ep"], c["offsets"], c["adj"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hostlib.search_per_query(tmp_path / "base.fbin", tmp_path / "g.index", c["test"], 10, 32)
