@@ -97,3 +97,31 @@ def test_pool_vs_ref(oracle, ref):
         dists = np.round(rng.standard_normal(nops), 1).astype(np.float32)
         a, b = oracle.pool_script(cap, kind, ids, dists), ref.pool_script(cap, kind, ids, dists)
         assert all((x == y).all() for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("metric,dim,n", [(1, 200, 6000), (0, 48, 4000), (1, 104, 3000)])
+def test_search_vs_ref_live(oracle, ref, tmp_path, metric, dim, n):
+    """Whole searches, oracle vs the compiled reference (IndexBipartite::SearchRoarGraph through its own loaders), on fresh
+    seeded random graphs incl. zero-degree nodes, duplicate neighbours and heavy ties: ids / dists / cmps / hops bit-equal."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(1000 + dim)
+    base = np.round(rng.standard_normal((n, dim)) * 2).astype(np.float32) / 2   # half-integers: many exact ties
+    queries = rng.standard_normal((150, dim)).astype(np.float32)
+    deg = rng.integers(0, 40, n)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=off[1:])
+    adj = rng.integers(0, n, int(off[-1])).astype(np.uint32)
+    ep = int(np.argmax(deg))
+    io.write_fbin(tmp_path / "b.fbin", base)
+    io.write_index(tmp_path / "g.index", ep, off, adj)
+    h = ref.open(str(tmp_path / "b.fbin"), str(tmp_path / "g.index"), metric=metric, threads=4)
+    try:
+        for L, k in ((1, 1), (10, 10), (33, 10), (200, 100)):
+            want = ref.search(h, queries, k, L, threads=4)
+            got = oracle.search(base, off, adj, ep, queries, k, L, metric=metric)
+            for key in ("ids", "cmps", "hops"):
+                assert (got[key] == want[key]).all(), (key, L)
+            assert (bits(got["dists"]) == bits(want["dists"])).all(), L
+    finally:
+        ref.close(h)
