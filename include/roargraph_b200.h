@@ -72,7 +72,9 @@ RG_API rg_status rg_index_info(const rg_index *index, uint64_t *n, uint32_t *dim
  * passed is page-locked host memory (cudaHostAlloc / cudaHostRegister) the kernel reads the queries and writes
  * the results through the mapped pointers (no staging copies); pageable buffers are staged ("zero_copy" option).
  * Returns RG_ERR_NOT_ENOUGH_RESULTS if any query ends with fewer than k pool entries (its ids
- * are filled with 0xFFFFFFFF), like the reference's std::runtime_error. */
+ * are filled with 0xFFFFFFFF), like the reference's std::runtime_error.
+ * Threading: an rg_index owns one stream and one set of scratch buffers, so calls on the SAME index must not overlap
+ * (the host class serialises them); different indices - e.g. one replica per GPU - may be searched concurrently. */
 RG_API rg_status rg_search_batch(rg_index *index, const float *queries, uint64_t nq, uint32_t k, uint32_t L,
                                  uint32_t *ids, float *dists, uint32_t *cmps, uint32_t *hops);
 /* Device variant: all buffers are device memory, work is enqueued on `cuda_stream` (a cudaStream_t,
