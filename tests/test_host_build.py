@@ -95,3 +95,38 @@ def test_search_without_gpu_fails_loudly(tmp_path):
     io.write_index(tmp_path / "g.index", c["ep"], c["offsets"], c["adj"])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hostlib.search_per_query(tmp_path / "base.fbin", tmp_path / "g.index", c["test"], 10, 32)
+
+
+def test_error_behaviour_matches_reference(tmp_path):
+    """Error paths of the loaders / driver as the reference has them (SURVEY.md 8b "Errors"): a truncated fbin raises
+    "Data file size wrong!" (util.h:124), an unopenable input file exits with status 255 (exit(-1), util.h:87-90), a kNN
+    file whose row count differs from the training set is rejected (src/index_bipartite.cpp:2635-2637), an unwritable
+    save path fails (:2608-2610)."""
+    c = load_case("ip_d24_norm")
+    p = lambda f: str(tmp_path / f)
+    io.write_fbin(p("base.fbin"), c["base"]); io.write_fbin(p("train.fbin"), c["train"])
+    io.write_ibin(p("nn.ibin"), c["knn_ids"], np.zeros(c["knn_ids"].shape, np.float32))
+    exe = os.path.join(hostlib.BIN_DIR, "test_build_roargraph")
+
+    def build(**over):
+        a = {"--base_data_path": p("base.fbin"), "--sampled_query_data_path": p("train.fbin"),
+             "--projection_index_save_path": p("out.index"), "--learn_base_nn_path": p("nn.ibin")}
+        a.update(over)
+        cmd = [exe, "--data_type", "float", "--dist", "ip", "--M_sq", str(c["M_sq"]), "--M_pjbp", str(c["M_pjbp"]),
+               "--L_pjpq", str(c["L_pjpq"]), "-T", "1"]
+        for k_, v in a.items():
+            cmd += [k_, v]
+        return subprocess.run(cmd, capture_output=True, text=True)
+
+    raw = open(p("base.fbin"), "rb").read()
+    open(p("short.fbin"), "wb").write(raw[: len(raw) // 2])
+    r = build(**{"--base_data_path": p("short.fbin")})
+    assert r.returncode != 0 and "Data file size wrong!" in (r.stderr + r.stdout)
+    r = build(**{"--base_data_path": p("does_not_exist.fbin")})
+    assert r.returncode == 255
+    io.write_ibin(p("bad_nn.ibin"), c["knn_ids"][:-3], np.zeros(c["knn_ids"][:-3].shape, np.float32))
+    r = build(**{"--learn_base_nn_path": p("bad_nn.ibin")})
+    assert r.returncode != 0
+    r = build(**{"--projection_index_save_path": p("no_such_dir/out.index")})
+    assert r.returncode != 0 and not os.path.exists(p("no_such_dir/out.index"))
+    assert "cannot open file" in (r.stderr + r.stdout)          # same what() as the reference's SaveProjectionGraph
