@@ -67,6 +67,54 @@ def gather_rows(local: torch.Tensor, bounds: List[int], group=None) -> torch.Ten
     return torch.cat([out[g, : bounds[g + 1] - bounds[g]] for g in range(world)], dim=0)
 
 
+class Grid:
+    """2-D decomposition of `world` ranks into `base_shards` x `query_groups`: rank r holds base shard r % base_shards and
+    answers query group r // base_shards; the exchange + merge of `knn_sharded` then runs inside each query group
+    (a process group of `base_shards` ranks).  base_shards == world is the plain base-sharded scheme of BASELINE.json's
+    config C4; base_shards == 1 shards the queries only (no exchange at all) - the better choice when a base shard would
+    be so small that the per-batch threshold warm-up of K2 dominates (1.25M-row shards reach 663
+    TFLOP/s per GPU, 5M-row shards 914)."""
+
+    def __init__(self, base_shards: int, world: Optional[int] = None, rank: Optional[int] = None):
+        world = dist.get_world_size() if world is None else world
+        rank = dist.get_rank() if rank is None else rank
+        if base_shards <= 0 or world % base_shards:
+            raise ValueError(f"base_shards={base_shards} must divide the world size {world}")
+        self.world, self.rank = world, rank
+        self.base_shards, self.query_groups = base_shards, world // base_shards
+        self.shard, self.qgroup = rank % base_shards, rank // base_shards
+        self.group = None
+
+    def make_groups(self):
+        """Collective: every rank creates every query group's process group (torch.distributed requires that) and keeps
+        its own.  Returns self."""
+        for g in range(self.query_groups):
+            ranks = list(range(g * self.base_shards, (g + 1) * self.base_shards))
+            pg = dist.new_group(ranks)
+            if g == self.qgroup:
+                self.group = pg
+        return self
+
+    def base_bounds(self, n: int) -> Tuple[int, int]:
+        b = shard_bounds(n, self.base_shards)
+        return b[self.shard], b[self.shard + 1]
+
+    def query_bounds(self, nq: int) -> Tuple[int, int]:
+        b = shard_bounds(nq, self.query_groups)
+        return b[self.qgroup], b[self.qgroup + 1]
+
+    def result_bounds(self, nq: int) -> List[int]:
+        """Row bounds, in rank order, of the merged slices the ranks end up with (gather=False): query group by query
+        group, inside a group slice by slice - contiguous and ascending, so `gather_rows(slice, bounds)` over the whole
+        world assembles the full answer."""
+        out = [0]
+        qb = shard_bounds(nq, self.query_groups)
+        for g in range(self.query_groups):
+            inner = shard_bounds(qb[g + 1] - qb[g], self.base_shards)
+            out += [qb[g] + v for v in inner[1:]]
+        return out
+
+
 def knn_sharded_with(local_knn: Callable, merge: Callable, queries: torch.Tensor, K: int, group=None,
                      gather: bool = True):
     """The sharded algorithm with the two compute steps injected (CUDA kernels in the product path, the oracle in the

@@ -89,3 +89,61 @@ def test_product_path_refuses_cpu_tensors():
 
     with pytest.raises(capi.RoarGraphError):
         sharded_knn.knn_sharded(torch.zeros(4, 8), 0, torch.zeros(2, 8), 2)
+
+
+def test_grid_layout():
+    g = sharded_knn.Grid(2, world=8, rank=5)
+    assert (g.base_shards, g.query_groups, g.shard, g.qgroup) == (2, 4, 1, 2)
+    assert g.base_bounds(10) == (5, 10) and g.query_bounds(103) == (52, 78)
+    assert sharded_knn.Grid(8, world=8, rank=3).query_bounds(100) == (0, 100)      # plain base sharding
+    assert sharded_knn.Grid(1, world=8, rank=3).base_bounds(100) == (0, 100)       # plain query sharding
+    rb = sharded_knn.Grid(2, world=4, rank=0).result_bounds(10)
+    assert rb == [0, 3, 5, 8, 10]
+    with pytest.raises(ValueError):
+        sharded_knn.Grid(3, world=8, rank=0)
+
+
+def _grid_worker(rank, world, port, base_shards, n, nq, dim, K, metric, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mysteryann_b200 import synth
+        from oracle.binding import Oracle
+
+        o = Oracle()
+        base, q, _ = synth.make_numpy(n, nq, 1, dim, seed=9)
+        grid = sharded_knn.Grid(base_shards).make_groups()
+        lo, hi = grid.base_bounds(n)
+        q0, q1 = grid.query_bounds(nq)
+        shard = base[lo:hi]
+
+        def local_knn(queries):
+            ids, d, _ = o.exact_knn(shard, queries.numpy(), K, metric=metric, threads=2)
+            ids = np.where(ids == 0xFFFFFFFF, ids, ids + np.uint32(lo))
+            return torch.from_numpy(ids.view(np.int32).copy()), torch.from_numpy(d.copy())
+
+        sid, sd, _ = sharded_knn.knn_sharded_with(local_knn, numpy_merge(metric), torch.from_numpy(q[q0:q1]), K,
+                                                  group=grid.group, gather=False)
+        rb = grid.result_bounds(nq)
+        assert sid.shape[0] == rb[rank + 1] - rb[rank]
+        ids = sharded_knn.gather_rows(sid, rb)          # over the whole world
+        d = sharded_knn.gather_rows(sd, rb)
+        want_ids, want_d, _ = o.exact_knn(base, q, K, metric=metric, threads=2)
+        assert np.array_equal(ids.numpy().view(np.uint32), want_ids), f"rank {rank}: ids differ"
+        assert np.array_equal(d.numpy().view(np.uint32), want_d.view(np.uint32)), f"rank {rank}: dists differ"
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,base_shards", [(4, 2), (4, 1), (4, 4), (2, 1)])
+def test_grid_knn_gloo(tmp_path, world, base_shards):
+    """2-D decomposition (base shards x query groups) on CPU: 2x2, query-only, base-only layouts give the full answer."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_grid_worker, args=(world, port, base_shards, 403, 29, 16, 7, 1, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
