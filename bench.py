@@ -46,11 +46,18 @@ def parse_args():
     ap.add_argument("--L_pjpq", type=int, default=500)
     ap.add_argument("--seed", type=int, default=20240430)
     ap.add_argument("--cache", default=os.environ.get("RG_BENCH_CACHE", "/tmp/rg_bench_cache"))
-    ap.add_argument("--cpu-sample", type=int, default=2000, help="queries timed on the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries timed on the CPU baseline (0 = the whole batch)")
+    ap.add_argument("--config", default="", choices=["", "C2", "C3", "C3k100", "C5"],
+                    help="canonical BASELINE.json workloads: C2 = 10M x 200 (default), C3 = 2.5M x 512 unit rows k=10, "
+                         "C3k100 = the same with k=100, C5 = 100M x 200 with 100K-query batches")
+    ap.add_argument("--knn-slice", type=int, default=262_144,
+                    help="training queries of the timed build-kNN slice (roofline_knn); 0 = skip")
+    ap.add_argument("--gt-check", type=int, default=128, help="ground-truth rows cross-checked against the CPU oracle at N=1")
     ap.add_argument("--gather", type=int, default=0)
     ap.add_argument("--stage-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per query (0 = library default)")
     ap.add_argument("--hash-space", type=int, default=0)
+    ap.add_argument("--stage-bufs", type=int, default=0, help="row staging buffers per warp (0 = library default)")
     ap.add_argument("--ctas", type=int, default=0, help="resident K1 CTAs per SM (0 = library default)")
     ap.add_argument("--hash-log2", type=int, default=0, help="visited-hash slots per query, log2 (0 = library default)")
     ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
@@ -58,7 +65,18 @@ def parse_args():
     ap.add_argument("--zero-copy", type=int, default=1, help="e2e: 1 = rg_search_batch works in place on the pinned host buffers, 0 = staged copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--normalize", action="store_true", help="L2-normalise all rows (CLIP-like config C3: --n 2500000 --dim 512)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    canon = {"C2": dict(n=10_000_000, dim=200, queries=10_000, k=10, normalize=False),
+             "C3": dict(n=2_500_000, dim=512, queries=10_000, k=10, normalize=True),
+             "C3k100": dict(n=2_500_000, dim=512, queries=10_000, k=100, normalize=True),
+             "C5": dict(n=100_000_000, dim=200, queries=100_000, k=10, normalize=False)}
+    for key, val in canon.get(a.config, {}).items():
+        setattr(a, key, val)
+    if a.config == "C5" and not a.train:
+        a.train = 5_000_000  # the build kNN at 100M rows costs 0.2 s per 1000 training queries on one GPU
+    if a.cpu_sample <= 0:
+        a.cpu_sample = a.queries
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -156,7 +174,9 @@ def prepare(args, rank, world, device):
         info = cached
     if world > 1:
         dist.barrier()
+    knn_slice = train[:min(args.knn_slice, n_train)].clone() if args.knn_slice else None
     del train
+    capi.knn_release_scratch()
     torch.cuda.empty_cache()
     if index is None:
         if os.path.exists(index_path + ".csr.npz"):
@@ -169,7 +189,9 @@ def prepare(args, rank, world, device):
         del offsets, adj
     q = test[rank * args.queries:(rank + 1) * args.queries].contiguous()
     gt, _ = gpu_exact_knn(base, q, args.k)
-    return dict(base=base, queries=q, gt=gt.cpu().numpy().astype(np.uint32), index=index, info=info, index_path=index_path)
+    capi.knn_release_scratch()
+    return dict(base=base, queries=q, gt=gt.cpu().numpy().astype(np.uint32), index=index, info=info, index_path=index_path,
+                knn_slice=knn_slice)
 
 
 def recall_at_k(ids, gt, k):
@@ -227,19 +249,111 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
+def load_tensor_peaks():
+    """(burst, sustained) dense bf16/fp16 TFLOP/s: MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 1640.9, 1378.6, "fallback"
+
+
+def k1_source_hash():
+    """Fingerprint of the K1 sources: a traffic figure taken from a committed ncu capture is only quoted while the kernel
+    it was captured from is the kernel that runs."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("rg_search.cu", "rg_distance.cuh", "rg_common.cuh"):
+        h.update(open(os.path.join(ROOT, "mysteryann_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic(args, L):
-    """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this same workload (profiles/k1_traffic.json:
-    dram__bytes_read.sum + dram__bytes_write.sum of one rg_search_kernel launch); None when the workload differs."""
+    """DRAM bytes per K1 launch (dram__bytes_read.sum + dram__bytes_write.sum of one rg_search_kernel launch) from the
+    committed `ncu --set full` capture of this same workload, profiles/k1_traffic.json (written by tools/make_k1_traffic.py).
+    ncu cannot run inside the timed bench, so the figure is FROM A PROFILE: it is quoted only when the workload matches and
+    the profile's K1 source fingerprint equals the running kernel's; otherwise (None, reason)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
         w = t["workload"]
         n_train = args.train or max(50_000, args.n // 5)
-        if (w["n_base"], w["dim"], w["queries"], w["L_pq"], w["k"], w.get("n_train", n_train)) == \
+        if (w["n_base"], w["dim"], w["queries"], w["L_pq"], w["k"], w.get("n_train", n_train)) != \
                 (args.n, args.dim, args.queries, L, args.k, n_train):
-            return int(t["dram_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+            return None, "profile is of another workload"
+        if t.get("k1_source_hash") != k1_source_hash():
+            return None, "profile is of another kernel version"
+        return int(t["dram_bytes_per_launch"]), "from_profile:profiles/k1_traffic.json"
+    except Exception as e:  # noqa: BLE001
+        return None, f"no profile ({type(e).__name__})"
+
+
+def time_knn_slice(args, d, rank, world, device):
+    """Build kNN (BASELINE.json's second metric) on a fixed slice: the first --knn-slice training queries against the whole
+    base, K = M_sq.  N = 1: rg_knn_exact_device; N > 1: the base sharded over the ranks, rg_knn_exact_sharded (K2/K3 per
+    shard, grouped ncclSend/ncclRecv, K4 merge).  CUDA events on the launching stream, max over ranks; one untimed
+    warm-up call (scratch allocation, NCCL channels)."""
+    import torch
+    import torch.distributed as dist
+
+    from mysteryann_b200 import capi, sharded_knn
+
+    q = d["knn_slice"]
+    if q is None or q.shape[0] == 0:
+        return None
+    base, K = d["base"], args.M_sq
+    st = torch.cuda.current_stream().cuda_stream
+    b = sharded_knn.shard_bounds(args.n, world)
+
+    def run(qq):
+        if world == 1:
+            ids = torch.empty((qq.shape[0], K), dtype=torch.int32, device=device)
+            dd = torch.empty((qq.shape[0], K), dtype=torch.float32, device=device)
+            capi.knn_exact_device(base, qq, K, ids, dd, metric=capi.METRIC_IP, stream=st)
+            return ids, dd
+        ids, dd, _ = sharded_knn.knn_sharded(base[b[rank]:b[rank + 1]], b[rank], qq, K, metric=capi.METRIC_IP, gather=False,
+                                             stream=st)
+        return ids, dd
+
+    run(q[:min(65536, q.shape[0])].contiguous())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ids, _ = run(q)
+    e1.record()
+    torch.cuda.synchronize()
+    stats = capi.knn_last_stats()
+    ms = e0.elapsed_time(e1)
+    # the merged slices must equal the unsharded kernels' answer (first rows of this rank's slice)
+    same = 1
+    if world > 1:
+        lo, hi = capi.knn_sharded_slice(q.shape[0], rank, world)
+        m = min(512, hi - lo)
+        want = torch.empty((m, K), dtype=torch.int32, device=device)
+        wd = torch.empty((m, K), dtype=torch.float32, device=device)
+        capi.knn_exact_device(base, q[lo:lo + m].contiguous(), K, want, wd, metric=capi.METRIC_IP, stream=st)
+        torch.cuda.synchronize()
+        same = int(torch.equal(want, ids[:m]))
+        t = torch.tensor([ms, float(1 - same), float(stats["second_pass"]), float(stats["exact_scans"])], device=device,
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, same = t[0].item(), int(t[1].item() == 0)
+        stats = dict(stats, second_pass_max_rank=int(t[2].item()), exact_scans_max_rank=int(t[3].item()))
+    capi.knn_release_scratch()
+    torch.cuda.empty_cache()
+    burst, sustained, kind = load_tensor_peaks()
+    nq = q.shape[0]
+    flops = 2.0 * nq * args.n * args.dim
+    per_gpu = flops / (ms * 1e-3) / 1e12 / world
+    return {"bound": "tensor", "achieved": round(per_gpu, 1), "peak": burst, "unit": "TFLOP/s per GPU",
+            "frac": round(per_gpu / burst, 4), "frac_of_sustained_peak": round(per_gpu / sustained, 4), "peak_kind": kind,
+            "kernel": "knn_gemm_filter_kernel (tcgen05 kind::f16) + select + FP32 re-rank" + (" + NCCL exchange + K4 merge" if world > 1 else ""),
+            "n_ranks": world, "shard_rows": b[1] - b[0], "queries": nq, "K": K, "knn_s": round(ms * 1e-3, 4),
+            "algorithmic_flops": flops, "c4_extrapolated_s": round(ms * 1e-3 * 10_000_000 / nq * (10_000_000 / args.n), 2),
+            "parallelism": "1 GPU" if world == 1 else f"base sharded over {world} GPUs, rg_knn_exact_sharded (grouped ncclSend/ncclRecv + K4 merge)",
+            "sharded_equals_unsharded": bool(same) if world > 1 else None, "knn_stats": stats}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -261,11 +375,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     d = prepare(args, rank, world, device)
+    roofline_knn = time_knn_slice(args, d, rank, world, device)  # BASELINE.json's "build kNN s", same slice at every N
+    d["knn_slice"] = None
     nq, k, dim = args.queries, args.k, args.dim
     ix = d["index"]
     ix.configure(gather=args.gather, warps_per_query=args.warps, ctas_per_sm=args.ctas, stage_rows=args.stage_rows,
                  hash_log2=args.hash_log2, hash_space=args.hash_space,
-                 l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch)
+                 l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch, stage_bufs=args.stage_bufs)
     ix.set_option("zero_copy", args.zero_copy)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)
@@ -278,24 +394,26 @@ def run_ours(args):
     def search(L):
         ix.search_device(q, k, L, ids, dists, cmps, hops, status, stream)
 
-    # ---- beam width: the smallest L of the sweep whose recall@k reaches the target --------------------
+    # ---- beam width: the smallest L of the sweep whose recall@k reaches the target, decided ONCE on rank 0's query set and
+    # used by every rank (round 1 took the max over per-rank choices, so N=4 timed another L than N=1/2/8)
     sweep = []
     L_sel = args.L
-    for L in ([args.L] if args.L else L_SWEEP):
-        if L < k:
-            continue
-        search(L)
-        torch.cuda.synchronize()
-        r = recall_at_k(ids.cpu().numpy().view(np.uint32), d["gt"], k)
-        sweep.append((L, round(r, 4)))
-        if not args.L and r >= args.recall:
-            L_sel = L
-            break
-    if not L_sel:
-        L_sel = L_SWEEP[-1]
-    if world > 1:  # all ranks time the same L: take the max over ranks
+    if rank == 0:
+        for L in ([args.L] if args.L else L_SWEEP):
+            if L < k:
+                continue
+            search(L)
+            torch.cuda.synchronize()
+            r = recall_at_k(ids.cpu().numpy().view(np.uint32), d["gt"], k)
+            sweep.append((L, round(r, 4)))
+            if not args.L and r >= args.recall:
+                L_sel = L
+                break
+        if not L_sel:
+            L_sel = L_SWEEP[-1]
+    if world > 1:
         t = torch.tensor([L_sel], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.broadcast(t, src=0)
         L_sel = int(t.item())
     search(L_sel)
     torch.cuda.synchronize()
@@ -366,6 +484,7 @@ def run_ours(args):
         ms_per_step = dev_ms / args.steps
         value = nq * world / (ms_per_step * 1e-3)
         alg_bytes = sum_cmps * dim * 4  # this rank's launch: gathered vector bytes
+        traffic, traffic_src = load_traffic(args, L_sel)
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         out = {
             "metric": "QPS at recall@10=0.9 (IP, OOD queries)", "value": round(value, 1), "unit": "queries/s",
@@ -384,13 +503,25 @@ def run_ours(args):
                                                                                 if args.zero_copy else "staged H2D + D2H copies") + ")"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": load_traffic(args, L_sel), "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": peak_kind, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                          "kernel": "rg_search_kernel", "algorithmic_bytes_per_launch": int(alg_bytes)},
             "clocks": sampler.summary(),
         }
+        if args.config:
+            out["config"]["canonical"] = args.config
+        if roofline_knn is not None:
+            out["roofline_knn"] = roofline_knn
+            out["config"]["knn_s"] = roofline_knn["knn_s"]
+            out["config"]["knn_parallelism"] = roofline_knn["parallelism"]
         if not args.no_cpu_baseline and world == 1:  # reported at N=1 only; --impl reference times it at every N
-            out["cpu_baseline"] = cpu_baseline(args, d, L_sel)
+            res_gpu = dict(ids=ids.cpu().numpy().view(np.uint32), dists=dists.cpu().numpy(),
+                           cmps=cmps.cpu().numpy().view(np.uint32), hops=hops.cpu().numpy().view(np.uint32))
+            out["cpu_baseline"], out["parity"] = cpu_baseline(args, d, L_sel, res_gpu)
         print(json.dumps(out), flush=True)
+        if "parity" in out and not out["parity"]["ok"]:
+            raise SystemExit("PARITY FAILURE: the GPU results differ from the reference's on the same inputs: "
+                             + json.dumps(out["parity"]))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -428,21 +559,72 @@ class CpuReference:
 
     def report(self, L, sample, res):
         return {"value": round(sample / res["seconds"], 1), "unit": "queries/s", "cores": self.threads, "kind": self.kind,
-                "sample": f"first {sample} of the {self.args.queries} queries, L_pq={L}, OpenMP schedule(dynamic,1) like "
-                          "tests/test_search_roargraph.cpp:203"}
+                "sample": (f"all {sample} queries" if sample == self.args.queries else f"first {sample} of the {self.args.queries} queries")
+                          + f", L_pq={L}, one cold pass, OpenMP schedule(dynamic,1) like tests/test_search_roargraph.cpp:203"}
 
     def close(self):
         if self.kind == "reference":
             self.r.close(self.h)
 
 
-def cpu_baseline(args, d, L):
+def compare_results(got, want):
+    """Bit-for-bit comparison of two result sets (ids, dists as bit patterns, cmps, hops) -> parity dict."""
+    n = len(want["ids"])
+    par = {"n": int(n)}
+    ok = True
+    for key in ("ids", "cmps", "hops"):
+        eq = bool((got[key][:n] == want[key][:n]).all())
+        par[key] = eq
+        ok = ok and eq
+    gb = np.ascontiguousarray(got["dists"][:n], np.float32).view(np.uint32)
+    wb = np.ascontiguousarray(want["dists"][:n], np.float32).view(np.uint32)
+    par["dists_bits"] = bool((gb == wb).all())
+    par["ok"] = ok and par["dists_bits"]
+    if not par["ok"]:
+        bad = np.argwhere((got["ids"][:n] != want["ids"][:n]).any(axis=1)).ravel()
+        par["first_bad_queries"] = [int(b) for b in bad[:5]]
+    return par
+
+
+def check_ground_truth(args, d, rows):
+    """The bench's recall is computed against ground truth from the repo's own K2-K4 kernels; cross-check its first `rows`
+    lists against the CPU oracle's exact_knn (FP32 brute force, compute_groundtruth.cpp:126-248 restated) on the full base.
+    ids must agree except where the two FP32 scores are within 1e-6 relative (the tie rule of BASELINE.json)."""
+    from oracle.binding import Oracle
+
+    o = Oracle()
+    base = d["base"].cpu().numpy()
+    q = d["queries"][:rows].cpu().numpy()
+    want_ids, want_d, sec = o.exact_knn(base, q, args.k, metric=1)
+    gt = d["gt"][:rows, :args.k]
+    diff = np.argwhere(gt != want_ids)
+    # a differing position is acceptable only on a near-tie: compare the oracle's score at that rank with the exact score
+    # of the id the GPU put there
+    worst = 0.0
+    for qi, j in diff:
+        mine = float(np.dot(base[gt[qi, j]].astype(np.float64), q[qi].astype(np.float64)))
+        ref = float(want_d[qi, j])
+        worst = max(worst, abs(mine - ref) / max(1.0, abs(ref)))
+    return {"rows": int(rows), "id_mismatches": int(len(diff)), "max_rel_score_gap_at_mismatch": worst,
+            "ok": bool(worst <= 1e-6), "oracle_seconds": round(sec, 2)}
+
+
+def cpu_baseline(args, d, L, res_gpu=None):
     ref = CpuReference(args, d)
     sample = min(args.cpu_sample, args.queries)
     res = ref.search(L, sample)
     out = ref.report(L, sample, res)
+    parity = None
+    if res_gpu is not None:
+        # the protocol of tests/test_search_roargraph.cpp:196-214 on the same index file and queries: the reference's
+        # ids / distances / (cmps, hops) against ours, every query of the sample, bit for bit
+        parity = compare_results(res_gpu, res)
+        parity["against"] = f"{ref.kind} SearchRoarGraph, first {sample} queries, L_pq={L}"
+        if args.gt_check:
+            parity["ground_truth_vs_oracle"] = check_ground_truth(args, d, min(args.gt_check, args.queries))
+            parity["ok"] = parity["ok"] and parity["ground_truth_vs_oracle"]["ok"]
     ref.close()
-    return out
+    return out, parity
 
 
 def run_reference(args):
@@ -458,14 +640,17 @@ def run_reference(args):
 
     build.build()
     device = torch.device("cuda", 0)
+    args.knn_slice = 0
     d = prepare(args, 0, 1, device)
     ref = CpuReference(args, d)
-    # same beam width rule as our arm: smallest L reaching the recall target (on the CPU sample)
+    # same beam width rule as our arm: smallest L of the sweep reaching the recall target on the same query batch
     L_sel = args.L
     sample = min(args.cpu_sample, args.queries)
     if not L_sel:
         for L in L_SWEEP:
-            res = ref.search(L, min(sample, 1000))
+            if L < args.k:
+                continue
+            res = ref.search(L, sample)
             if recall_at_k(res["ids"], d["gt"][:len(res["ids"])], args.k) >= args.recall:
                 L_sel = L
                 break
@@ -484,7 +669,9 @@ def run_reference(args):
            "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.n}x{args.dim} fp32 IP base, {args.queries} OOD queries, k={args.k}, "
-                                  f"L_pq={L_sel}; each step = {sample}-query sample on {cb['cores']} host threads",
+                                  f"L_pq={L_sel}; each step = " + ("the whole batch" if sample == args.queries else f"a {sample}-query sample")
+                                  + f" on {cb['cores']} host threads",
+                      "same_config": sample == args.queries,
                       "n_base": args.n, "dim": args.dim, "k": args.k, "L_pq": L_sel, "index": d["info"]},
            "cpu_baseline": cb,
            "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

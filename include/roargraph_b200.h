@@ -88,10 +88,13 @@ RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries,
  * mbarrier); warps_per_query: warps of the CTA that owns a query (1..8); stage_rows: rows per warp staging buffer. */
 RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
                                      int hash_log2);
-/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory (L2-resident slab per CTA);
+/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory with 32-bit keys (L2-resident
+ * slab per CTA), 3 in global memory with 16-bit quotient entries where the id range allows (what auto picks);
+ * "stage_bufs" = 0 auto, 1 or 2 row staging buffers per warp (2: the next batch of rows is in flight while one is scored);
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
- * (default 3): 1 = L2-prefetch the adjacency row of the next unexpanded pool entry, 2 = of scored candidates that beat it;
+ * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its
+ * neighbours into L2, 2 = L2-prefetch the adjacency rows of scored candidates that beat it;
  * "zero_copy" (default 1): rg_search_batch works straight on page-locked caller buffers, 0 = always stage through HBM. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Page-lock (and map) a caller-owned host buffer so that rg_search_batch can work on it without staging copies - what
@@ -112,7 +115,10 @@ RG_API uint64_t rg_index_launch_count(const rg_index *index);
  * (compute_groundtruth.cpp:438-441).  Host buffers. */
 RG_API rg_status rg_knn_exact(const float *base, uint64_t n, uint64_t id_base, const float *queries, uint64_t nq,
                               uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists, int device);
-/* Device variant, asynchronous on cuda_stream. */
+/* Device variant: all buffers are device memory on `device`; the kernels are enqueued on cuda_stream and the call returns
+ * after synchronising that stream (the operand scale factors are read back at the start and the number of queries
+ * without a completeness certificate at the end; nothing synchronises per query batch).  Scratch (FP16 operand copies,
+ * candidate lists: ~5 GB for a 10M x 200 shard) is cached per device between calls: rg_knn_release_scratch(). */
 RG_API rg_status rg_knn_exact_device(const float *d_base, uint64_t n, uint64_t id_base, const float *d_queries,
                                      uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *d_ids,
                                      float *d_dists, int device, void *cuda_stream);
@@ -129,8 +135,41 @@ RG_API rg_status rg_knn_merge(const uint32_t *part_ids, const float *part_dists,
                               int metric, uint32_t *ids, float *dists, int device);
 
 /* Diagnostics of the last rg_knn_exact* call of the calling thread: kernel launches issued, and how many queries
- * failed the completeness certificate and were redone by the exact FP32 scan. */
+ * failed the completeness certificate twice and were redone by the exact FP32 scan. */
 RG_API void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans);
+/* ... and how many queries failed it under the optimistic threshold schedule and were re-run with the conservative one
+ * (DESIGN.md "K2": expected to be a handful per million on rows in arbitrary order). */
+RG_API uint64_t rg_knn_last_second_pass_count(void);
+/* Frees the per-device scratch kept by rg_knn_exact_device (device < 0: every device). */
+RG_API rg_status rg_knn_release_scratch(int device);
+
+/* ---- exact kNN, base sharded over the GPUs of one box (build time) ------------------------------
+ * Replaces the part loop + merge of compute_groundtruth.cpp:396-448 (there: 20M-point parts walked sequentially on one
+ * host, per-part top-k concatenated and re-sorted).  `world` ranks - one per GPU; processes under torchrun or threads of
+ * one process - each hold one base shard (d_base_shard, n_shard rows, global id of row 0 = id_base) and ALL nq queries
+ * in device memory.  Rank r ends up with the merged global top-K of the contiguous query slice rg_knn_sharded_slice(nq,
+ * r, world) in d_ids / d_dists ([slice rows][K], same conventions as rg_knn_exact).  Per chunk of queries: K2/K3 on the
+ * local shard, ONE grouped ncclSend/ncclRecv exchange of the per-shard lists over NVLink (rank r receives the lists of
+ * its slice), K4 merge on the device.  nccl_comm is an ncclComm_t of exactly `world` ranks in which this caller is
+ * `rank` (NULL only when world == 1); every rank of the communicator must make the call with the same nq, dim, K and
+ * metric.  NCCL is resolved at run time from the libnccl.so.2 already loaded in the process (e.g. torch's) or the system
+ * one; the helpers below create a communicator without the caller linking NCCL itself. */
+RG_API rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shard, uint64_t id_base,
+                                      const float *d_queries, uint64_t nq, uint32_t dim, int metric, uint32_t K,
+                                      uint32_t *d_ids, float *d_dists, void *nccl_comm, int rank, int world,
+                                      int device, void *cuda_stream);
+/* Query rows [*lo, *hi) whose merged lists rank `rank` of `world` receives (contiguous, ascending with the rank; the first
+ * nq % world slices hold one extra row). */
+RG_API void rg_knn_sharded_slice(uint64_t nq, int rank, int world, uint64_t *lo, uint64_t *hi);
+/* ncclGetUniqueId / ncclCommInitRank / ncclCommInitAll / ncclCommDestroy through the run-time binding: id128 is the
+ * 128-byte ncclUniqueId (created on one rank, handed to the others by whatever side channel the host program has);
+ * rg_nccl_comm_init_all builds the ndev communicators of a one-process, thread-per-GPU program (devices may be NULL =
+ * 0..ndev-1).  rg_nccl_version() returns the NCCL version code in use (0 when NCCL cannot be loaded). */
+RG_API rg_status rg_nccl_get_unique_id(void *id128);
+RG_API rg_status rg_nccl_comm_init_rank(void **comm, int world, int rank, const void *id128, int device);
+RG_API rg_status rg_nccl_comm_init_all(void **comms, int ndev, const int *devices);
+RG_API rg_status rg_nccl_comm_destroy(void *comm);
+RG_API int rg_nccl_version(void);
 
 /* ---- graph construction on the GPU (build time) ---------------------------------------------------
  * Replaces the CPU phases of IndexBipartite::BuildRoarGraph (src/index_bipartite.cpp:143-233) and LinkProjection

@@ -8,7 +8,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libroargraph_b200.so")
-SOURCES = ["rg_index.cu", "rg_search.cu", "rg_knn.cu", "rg_build.cu"]
+SOURCES = ["rg_index.cu", "rg_search.cu", "rg_knn.cu", "rg_knn_sharded.cu", "rg_build.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
          "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

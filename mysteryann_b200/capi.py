@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libroargraph_b200.so")
+LIB_PATH = os.environ.get("RG_B200_LIB") or os.path.join(PKG, "libroargraph_b200.so")  # RG_B200_LIB: A/B builds (tools/)
 
 RG_OK = 0
 RG_ERR_NOT_ENOUGH_RESULTS = 3
@@ -23,7 +23,9 @@ SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_i
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
            "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
-           "rg_index_create_from_graph"]
+           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded",
+           "rg_knn_sharded_slice", "rg_nccl_get_unique_id", "rg_nccl_comm_init_rank", "rg_nccl_comm_init_all",
+           "rg_nccl_comm_destroy", "rg_nccl_version"]
 
 _lib = None
 
@@ -78,6 +80,23 @@ def lib():
     L.rg_knn_merge.argtypes = [vp, vp, u32, u64, u32, i32, vp, vp, i32]
     L.rg_knn_last_stats.restype = None
     L.rg_knn_last_stats.argtypes = [vp, vp]
+    L.rg_knn_last_second_pass_count.restype = u64
+    L.rg_knn_last_second_pass_count.argtypes = []
+    L.rg_knn_release_scratch.restype = i32
+    L.rg_knn_release_scratch.argtypes = [i32]
+    L.rg_knn_exact_sharded.restype = i32
+    L.rg_knn_exact_sharded.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32, vp]
+    L.rg_knn_sharded_slice.restype = None
+    L.rg_knn_sharded_slice.argtypes = [u64, i32, i32, vp, vp]
+    L.rg_nccl_get_unique_id.restype = i32
+    L.rg_nccl_get_unique_id.argtypes = [vp]
+    L.rg_nccl_comm_init_rank.restype = i32
+    L.rg_nccl_comm_init_rank.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
+    L.rg_nccl_comm_init_all.restype = i32
+    L.rg_nccl_comm_init_all.argtypes = [vp, i32, vp]
+    L.rg_nccl_comm_destroy.restype = i32
+    L.rg_nccl_comm_destroy.argtypes = [vp]
+    L.rg_nccl_version.restype = i32
     L.rg_build_roargraph_device.restype = i32
     L.rg_build_roargraph_device.argtypes = [vp, u64, u32, i32, vp, u64, u32, u32, u32, u32, C.POINTER(vp), i32, vp]
     L.rg_graph_info.restype = i32
@@ -148,16 +167,17 @@ class Index:
     __del__ = close
 
     def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0,
-                  l2_hint=None, adj_prefetch=None):
+                  l2_hint=None, adj_prefetch=None, stage_bufs=0):
         _check(lib().rg_search_configure(self._h, gather, warps_per_query, ctas_per_sm, stage_rows, hash_log2))
         _check(lib().rg_search_set_option(self._h, b"hash_space", hash_space))
+        _check(lib().rg_search_set_option(self._h, b"stage_bufs", stage_bufs))
         if l2_hint is not None:
             _check(lib().rg_search_set_option(self._h, b"l2_hint", l2_hint))
         if adj_prefetch is not None:
             _check(lib().rg_search_set_option(self._h, b"adj_prefetch", adj_prefetch))
 
     def set_option(self, name: str, value: int):
-        """Named option of rg_search_set_option ("hash_space", "l2_hint", "adj_prefetch", "zero_copy")."""
+        """Named option of rg_search_set_option ("hash_space", "stage_bufs", "l2_hint", "adj_prefetch", "zero_copy")."""
         _check(lib().rg_search_set_option(self._h, name.encode(), int(value)))
 
     @property
@@ -258,4 +278,38 @@ def knn_merge_device(d_part_ids, d_part_dists, d_ids, d_dists, metric=METRIC_IP,
 def knn_last_stats():
     a, b = C.c_uint64(0), C.c_uint64(0)
     lib().rg_knn_last_stats(C.byref(a), C.byref(b))
-    return dict(launches=a.value, exact_scans=b.value)
+    return dict(launches=a.value, exact_scans=b.value, second_pass=int(lib().rg_knn_last_second_pass_count()))
+
+
+def knn_release_scratch(device=-1):
+    _check(lib().rg_knn_release_scratch(device))
+
+
+def knn_sharded_slice(nq, rank, world):
+    lo, hi = C.c_uint64(0), C.c_uint64(0)
+    lib().rg_knn_sharded_slice(nq, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().rg_nccl_get_unique_id(buf))
+    return buf.raw
+
+
+def nccl_comm_init_rank(world, rank, unique_id: bytes, device):
+    h = C.c_void_p()
+    _check(lib().rg_nccl_comm_init_rank(C.byref(h), world, rank, C.c_char_p(unique_id), device))
+    return h
+
+
+def nccl_comm_destroy(comm):
+    _check(lib().rg_nccl_comm_destroy(comm))
+
+
+def knn_exact_sharded(d_base_shard, id_base, d_queries, K, d_ids, d_dists, comm, rank, world, metric=METRIC_IP, stream=None):
+    """rg_knn_exact_sharded on CUDA torch tensors; d_ids/d_dists hold this rank's query slice (knn_sharded_slice)."""
+    n, dim = d_base_shard.shape
+    device = d_base_shard.device.index or 0
+    _check(lib().rg_knn_exact_sharded(d_base_shard.data_ptr(), n, id_base, d_queries.data_ptr(), d_queries.shape[0], dim,
+                                      metric, K, d_ids.data_ptr(), d_dists.data_ptr(), comm, rank, world, device, stream))

@@ -619,32 +619,48 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     pp.heads = heads;
     double t_search = 0, t_prune = 0;
     rg_status status = RG_OK;
+    // every failure inside the loop becomes a status (the scratch of `view` is released on all paths below): a wave that
+    // dropped out silently would leave part of the nodes without their connectivity edges and still return RG_OK
+    auto cuda_fail = [&](cudaError_t e, const char *what) {
+        status = rg::fail(e == cudaErrorMemoryAllocation ? RG_ERR_OUT_OF_MEMORY : RG_ERR_CUDA, "connectivity enhancement: %s failed: %s", what,
+                          cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return false;
+    };
+#define RG_WAVE_OK(expr)                                   \
+    {                                                      \
+        const cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess && !cuda_fail(_e, #expr)) break; \
+    }
     for (uint64_t lo = 0; lo < n && status == RG_OK; lo += wave) {
         const uint32_t count = uint32_t(std::min<uint64_t>(wave, n - lo));
         t0 = now_s();
         status = search_expanded_device(&view, uint32_t(lo), count, L_pjpq, exp_keys, exp_cnt, exp_cap, st);
         if (status != RG_OK) break;
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        RG_WAVE_OK(cudaStreamSynchronize(st));
         t_search += now_s() - t0;
         t0 = now_s();
         pp.node_lo = uint32_t(lo);
-        if (run_prune(kBaseSearchKeys, count) != cudaSuccess) break;
-        cudaMemsetAsync(cnt, 0, 16 * sizeof(uint32_t), st);
+        RG_WAVE_OK(run_prune(kBaseSearchKeys, count));
+        RG_WAVE_OK(cudaMemsetAsync(cnt, 0, 16 * sizeof(uint32_t), st));
         supply_append_kernel<<<(count + 7) / 8, 256, 0, st>>>(S, stride, 2 * M, uint32_t(lo), count, ovf, cnt, ovf_cap);
-        cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        RG_WAVE_OK(cudaGetLastError());
+        RG_WAVE_OK(cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        RG_WAVE_OK(cudaStreamSynchronize(st));
         const uint32_t n_ovf = std::min(h_cnt[0], ovf_cap);
         if (n_ovf) {
-            cub::DeviceRadixSort::SortKeys(cub_tmp, sort_bytes, ovf, ovf_sorted, uint64_t(n_ovf), 0, 64, st);
+            RG_WAVE_OK(cub::DeviceRadixSort::SortKeys(cub_tmp, sort_bytes, ovf, ovf_sorted, uint64_t(n_ovf), 0, 64, st));
             segment_heads_kernel<<<(n_ovf + 255) / 256, 256, 0, st>>>(ovf_sorted, n_ovf, heads, cnt + 1);
-            cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
-            if (cudaStreamSynchronize(st) != cudaSuccess) break;
+            RG_WAVE_OK(cudaGetLastError());
+            RG_WAVE_OK(cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+            RG_WAVE_OK(cudaStreamSynchronize(st));
             pp.n_pairs = n_ovf;
-            if (run_prune(kInternal, h_cnt[1]) != cudaSuccess) break;
+            RG_WAVE_OK(run_prune(kInternal, h_cnt[1]));
         }
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        RG_WAVE_OK(cudaStreamSynchronize(st));
         t_prune += now_s() - t0;
     }
+#undef RG_WAVE_OK
     cudaFree(view.d_overflow_list);
     cudaFree(view.d_ghash);
     view.d_overflow_list = nullptr;
@@ -697,6 +713,9 @@ rg_status rg_build_roargraph_device(const float *d_base, uint64_t n, uint32_t di
     if (n == 0 || n >= (1ull << 31) || n_train == 0 || n_train >= (1ull << 32) - 1)
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_roargraph_device: sizes out of range");
     if (dim == 0 || dim % 8 != 0) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_roargraph_device: dim must be a multiple of 8");
+    if (n_train * 2ull * M_pjbp >= (1ull << 32))  // segment_heads_kernel stores pair offsets as 32-bit words
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_roargraph_device: n_train * 2 * M_pjbp must stay below 2^32 (got %llu x 2 x %u)",
+                        (unsigned long long)n_train, M_pjbp);
     if (knn_k == 0 || M_sq == 0 || M_pjbp == 0 || M_pjbp > 64 || L_pjpq == 0 || L_pjpq > 8192)
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_roargraph_device: need knn_k, M_sq >= 1, 1 <= M_pjbp <= 64, 1 <= L_pjpq <= 8192");
     if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");

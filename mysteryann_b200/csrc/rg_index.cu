@@ -79,6 +79,12 @@ rg_status rg_index_create(rg_index **out, const float *base, uint64_t n, uint32_
         if (d > max_deg) max_deg = uint32_t(d);
     }
     uint64_t nnz = adj_offsets[n];
+    // neighbour ids index the base rows on the device (TMA gathers): a foreign or truncated index file must fail here,
+    // not as an out-of-bounds copy inside K1
+    for (uint64_t i = 0; i < nnz; ++i)
+        if (adj[i] >= n)
+            return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_index_create: neighbour id %u (adjacency entry %llu) out of range [0, %llu)", adj[i],
+                            (unsigned long long)i, (unsigned long long)n);
 
     rg::DeviceGuard guard(device);
     if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
@@ -160,7 +166,6 @@ rg_status rg_index_destroy(rg_index *ix) {
     cudaFree(ix->d_dists);
     cudaFree(ix->d_cmps);
     cudaFree(ix->d_hops);
-    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     cudaGetLastError();
     delete ix;
@@ -184,8 +189,19 @@ rg_status rg_host_register(void *ptr, uint64_t bytes) {
     if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
     cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        // fine only when the WHOLE range is already page-locked and mapped contiguously (a buffer that merely shares its
+        // first page with a registered neighbour must not be taken for pinned memory: rg_search_batch would write past
+        // the registered page); otherwise report it so that the caller keeps the staged path
         cudaGetLastError();
-        return RG_OK;
+        cudaPointerAttributes a0, a1;
+        if (cudaPointerGetAttributes(&a0, ptr) == cudaSuccess &&
+            cudaPointerGetAttributes(&a1, static_cast<char *>(ptr) + bytes - 1) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+            a1.type == cudaMemoryTypeHost &&
+            static_cast<char *>(a1.devicePointer) - static_cast<char *>(a0.devicePointer) == ptrdiff_t(bytes - 1))
+            return RG_OK;
+        cudaGetLastError();
+        return rg::fail(RG_ERR_CUDA, "cudaHostRegister(%llu bytes): the range overlaps another registration and is not fully page-locked",
+                        (unsigned long long)bytes);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -227,8 +243,14 @@ rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_query, int
 rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
     if (!ix || !name) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: null argument");
     if (!strcmp(name, "hash_space")) {
-        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory) or 2 (global memory)");
+        if (value < 0 || value > 3)
+            return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory), 2 (global memory, 32-bit keys) or 3 (global memory, 16-bit quotient entries when the id range allows)");
         ix->cfg_hash_space = value;
+        return RG_OK;
+    }
+    if (!strcmp(name, "stage_bufs")) {
+        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_bufs must be 0 (auto), 1 or 2");
+        ix->cfg_stage_bufs = value;
         return RG_OK;
     }
     if (!strcmp(name, "l2_hint")) {

@@ -25,10 +25,14 @@
 #include <mutex>
 #include <vector>
 
-#include "rg_common.cuh"
+#include "rg_knn.cuh"
+
+static thread_local uint64_t g_knn_stats[3] = {0, 0, 0};  // per calling thread (one host thread per GPU in the tools)
 
 namespace rg {
 namespace knn {
+
+void set_last_stats(const uint64_t stats[3]) { memcpy(g_knn_stats, stats, sizeof(g_knn_stats)); }
 
 constexpr int kTileM = 128;      // queries per CTA (its 128 TMEM lanes); the CTA pair's MMA covers 2 x 128
 constexpr int kHalfN = 128;      // base rows each CTA of the pair stages per tile
@@ -670,7 +674,11 @@ __global__ void __launch_bounds__(128) knn_select_kernel(uint64_t *cand, uint32_
 // ---------------------------------------------------------------------------------------------------------------
 // K3: exact FP32 re-rank (reference lane order, same arithmetic as the search kernel) + certificate
 // ---------------------------------------------------------------------------------------------------------------
-// 4 lanes per row, 8 rows per warp step; returns the lane-ordered sum (IP: dot, L2: squared distance) in lane 4g
+// 4 lanes per row, 8 rows per warp step; returns the lane-ordered sum (IP: dot, L2: squared distance) in lane 4g.
+// The row is streamed in chunks of 8 steps (8 x 16 B per lane, all loads issued before the first use), so a warp keeps
+// 8 rows x 512 B in flight instead of one 64-byte segment per row: K3 is a gather of k' random rows per query and was
+// latency-bound with one load per step (6.4 ms per 131072-query batch against a ~2.5 ms HBM floor).  The arithmetic and
+// its order are unchanged.
 template <bool kIP>
 __device__ __forceinline__ float exact_score(const float *__restrict__ a, const float *__restrict__ b, uint32_t dim,
                                              uint32_t t) {
@@ -679,19 +687,31 @@ __device__ __forceinline__ float exact_score(const float *__restrict__ a, const 
     const uint32_t n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t s = 0; s < n16; ++s) {
-        const float4 v = ap[4 * s], q = bp[4 * s];
-        if (kIP) {
-            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
-        } else {
-            const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z), dw = __fsub_rn(v.w, q.w);
-            acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
+    for (uint32_t s0 = 0; s0 < n16; s0 += 8) {
+        float4 vv[8], qq[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+            if (s0 + j < n16) vv[j] = __ldg(ap + 4 * (s0 + j));
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+            if (s0 + j < n16) qq[j] = __ldg(bp + 4 * (s0 + j));
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (s0 + j < n16) {
+                const float4 v = vv[j], q = qq[j];
+                if (kIP) {
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, q.x));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, q.y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, q.z));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, q.w));
+                } else {
+                    const float dx = __fsub_rn(v.x, q.x), dy = __fsub_rn(v.y, q.y), dz = __fsub_rn(v.z, q.z), dw = __fsub_rn(v.w, q.w);
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(dx, dx));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(dy, dy));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(dz, dz));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(dw, dw));
+                }
+            }
         }
     }
     float4 m;
@@ -728,7 +748,7 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float *__restrict
                                                           uint32_t dim, uint64_t id_base, const uint64_t *__restrict__ cand,
                                                           const uint32_t *__restrict__ cand_count, const float *__restrict__ thr,
                                                           const uint32_t *__restrict__ overflow, float eps_factor,
-                                                          float max_bnorm2, uint32_t nq, uint32_t K, uint32_t kprime, uint64_t n_base,
+                                                          float max_bnorm2, uint32_t nq, uint32_t K, uint64_t n_base,
                                                           uint32_t *__restrict__ out_ids, float *__restrict__ out_dists,
                                                           uint32_t *__restrict__ need_exact) {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -761,7 +781,8 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float *__restrict
         const float tau = thr[q] + (kIP ? 0.f : qq);
         const float eps = eps_factor * qn + 1e-5f * (qq + max_bnorm2);  // FP16 rounding bound + FP32 evaluation slack
         const float eK = ordered_to_float(uint32_t(s[K - 1] >> 31));
-        complete = (n >= kprime) && (eK < tau - eps) && overflow[q] == 0;
+        // n >= K survivors whose K-th exact score is clear of every non-survivor's lower bound: the top K is complete
+        complete = (eK < tau - eps) && overflow[q] == 0;
     }
     for (uint32_t i = lane; i < K; i += 32) {
         if (i < n) {
@@ -843,12 +864,6 @@ __global__ void __launch_bounds__(256) knn_exact_scan_kernel(const float *__rest
         }
         __syncthreads();
     }
-}
-
-__global__ void compact_flags_kernel(const uint32_t *__restrict__ flags, uint32_t n, uint32_t *__restrict__ list,
-                                     uint32_t *__restrict__ count) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flags[i]) list[atomicAdd(count, 1u)] = i;
 }
 
 __global__ void fill_f32_kernel(float *p, uint64_t n, float v) {
@@ -951,13 +966,115 @@ struct Scratch {
     }
 };
 
+// Per-device scratch cache.  rg_knn_exact_device used to cudaMalloc / cudaFree ~4.5 GB (10M-row shard) on every call, which
+// serialises with everything else on the device and showed up as 0.25-0.7 s outliers between back-to-back calls; the
+// buffers are now kept (grow-only) until rg_knn_release_scratch().  One call at a time per device (the mutex is held for
+// the whole call; the tools run one host thread per GPU).
+struct DeviceScratch {
+    std::mutex mu;
+    enum { kSlots = 24 };
+    void *ptr[kSlots] = {nullptr};
+    uint64_t cap[kSlots] = {0};
+    // FP16 copy of the last base shard converted on this device (valid while the caller keeps the rows unchanged: only
+    // reused inside one rg_knn_exact_sharded call, which runs K2 once per query segment against the same shard)
+    const float *prep_base = nullptr;
+    uint64_t prep_n = 0;
+    uint32_t prep_dim = 0;
+    float prep_scale = 0.f, prep_max_bnorm2 = 0.f;
+    template <typename T>
+    cudaError_t get(int slot, T **out, uint64_t count) {
+        const uint64_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
+        if (cap[slot] < bytes) {
+            if (ptr[slot]) cudaFree(ptr[slot]);
+            ptr[slot] = nullptr;
+            cap[slot] = 0;
+            cudaError_t e = cudaMalloc(&ptr[slot], bytes);
+            if (e != cudaSuccess) return e;
+            cap[slot] = bytes;
+        }
+        *out = static_cast<T *>(ptr[slot]);
+        return cudaSuccess;
+    }
+    void release() {
+        for (int i = 0; i < kSlots; ++i) {
+            if (ptr[i]) cudaFree(ptr[i]);
+            ptr[i] = nullptr;
+            cap[i] = 0;
+        }
+        prep_base = nullptr;
+    }
+};
+static DeviceScratch &device_scratch(int dev) {
+    static DeviceScratch all[64];
+    return all[dev & 63];
+}
+void release_scratch(int dev) {
+    DeviceScratch &d = device_scratch(dev);
+    std::lock_guard<std::mutex> lock(d.mu);
+    d.release();
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n_idx, uint32_t dim,
+                                   float *__restrict__ dst) {
+    const uint32_t c4 = dim >> 2;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < uint64_t(n_idx) * c4; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t r = uint32_t(i / c4), c = uint32_t(i % c4);
+        reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src + uint64_t(idx[r]) * dim)[c];
+    }
+}
+// rows of (src_ids, src_d) [n_idx][K] -> rows idx[r] of (dst_ids, dst_d)
+__global__ void scatter_results_kernel(const uint32_t *__restrict__ src_ids, const float *__restrict__ src_d,
+                                       const uint32_t *__restrict__ idx, uint32_t n_idx, uint32_t K,
+                                       uint32_t *__restrict__ dst_ids, float *__restrict__ dst_d) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < uint64_t(n_idx) * K; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t r = uint32_t(i / K), c = uint32_t(i % K);
+        dst_ids[uint64_t(idx[r]) * K + c] = src_ids[i];
+        dst_d[uint64_t(idx[r]) * K + c] = src_d[i];
+    }
+}
+// appends q_off + i for every flagged i (the order is irrelevant)
+__global__ void append_flags_kernel(const uint32_t *__restrict__ flags, uint32_t n, uint32_t q_off, uint32_t *__restrict__ list,
+                                    uint32_t *__restrict__ count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) list[atomicAdd(count, 1u)] = q_off + i;
+}
+
+static uint64_t env_u64(const char *name, uint64_t dflt, uint64_t lo, uint64_t hi) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return uint64_t(v < (long long)lo ? lo : (v > (long long)hi ? hi : v));
+}
+
+// Threshold schedule.  The base is visited in blocks of growing size; after each block K2s tightens the per-query threshold
+// tau and compacts the candidate list to the entries at or below it.
+//   conservative: tau = the k'-th best score seen so far.  Always certifiable, but the expected number of list insertions
+//                 at row i is k'/i: with k' = 150 the epilogue's hit path stays busy until ~1M rows have been seen, and a
+//                 1.25M-row shard (C4 on 8 GPUs) never gets out of it (round 1: 663 TFLOP/s per GPU against 1090 on one).
+//   optimistic  : tau = the r-th best score seen so far with r = clamp(ceil(c k' seen / n), r_min, k') - an estimate of
+//                 the (c k')-th best score of the WHOLE shard (rows in storage order are treated as a sample; c = 3,
+//                 r_min = 16).  Insertions drop to r/i per row, every block after the first few runs at the sparse
+//                 epilogue's speed, and the final list (~c k' entries) is cut to the k' best by the last select.  tau only
+//                 ever decreases, every non-survivor was rejected against a tau >= the final one, so the K3 certificate
+//                 (exact_K < tau - eps) is exactly as strong as before; what changes is that a query whose estimate was too
+//                 tight ends with too few survivors and FAILS the certificate.  Those queries are re-run with the
+//                 conservative schedule (and only what fails that goes to the exact FP32 scan), so the result is exact
+//                 for any row order - the row order only decides how many queries need the second pass.
+struct PassOutput {
+    uint32_t *ids;
+    float *dists;
+    uint32_t *flag_list;   // pass-local query indices that failed the certificate
+    uint32_t *flag_count;
+};
+
 rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const float *d_queries, uint64_t nq, uint32_t dim,
-                     int metric, uint32_t K, uint32_t *d_ids, float *d_dists, cudaStream_t st, uint64_t *stats) {
+                     int metric, uint32_t K, uint32_t *d_ids, float *d_dists, cudaStream_t st, uint64_t *stats, bool reuse_base) {
     if (!d_base || !d_queries || !d_ids || !d_dists) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: null argument");
     if (dim == 0 || dim % 8 != 0 || dim > kMaxSlabs * kSlabK)
         return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: dim must be a multiple of 8 in [8, %d]", kMaxSlabs * kSlabK);
     if (K == 0 || K > 128) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: K must be in [1, 128]");
     if (n == 0 || n >= (1ull << 31)) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: shard size must be in [1, 2^31)");
+    if (nq >= (1ull << 32)) return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: too many queries in one call");
     if (metric != RG_METRIC_L2 && metric != RG_METRIC_INNER_PRODUCT && metric != RG_METRIC_COSINE)
         return fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact: unsupported metric %d", metric);
     if (nq == 0) return RG_OK;
@@ -970,13 +1087,16 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         else if (rem > 16) tail_k = 32;
         else if (rem > 0) tail_k = 16;
     }
-    const uint32_t nslab = n_full + (tail_k ? 1 : 0);
     const uint32_t tail_bytes = kTileN * tail_k * 2;
     const uint32_t a_bytes = (n_full * kSlabBytes + tail_bytes + 1023) / 1024 * 1024;
     const uint64_t b_rows_pad = (n + kPairN - 1) / kPairN * kPairN;
     const uint32_t kprime = std::min<uint32_t>(256, std::max<uint32_t>(K + K / 2, K + 32));
-    const uint64_t q_batch = 32768;
-    const uint64_t q_rows_pad = (std::min(nq, q_batch) + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
+    // queries per batch: the candidate lists take 8 KB per query (1 GB at 131072); larger batches give the small early
+    // blocks 4x the M tiles of round 1's 32768 and quarter the number of per-batch launches
+    const uint64_t q_batch = std::min<uint64_t>(env_u64("RG_KNN_QBATCH", 131072, 256, 1u << 20), (nq + 255) / 256 * 256);
+    const uint64_t q_rows_pad = (q_batch + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
+    const bool optimistic = env_u64("RG_KNN_OPTIMISTIC", 1, 0, 1) != 0;
+    const uint64_t r_min = env_u64("RG_KNN_RMIN", 16, 1, 256), c_safety = env_u64("RG_KNN_SAFETY", 3, 1, 6);
     int dev = 0, sms = 0, smem_max = 0;
     RG_CUDA_OK(cudaGetDevice(&dev));
     RG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -991,41 +1111,52 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
         fprintf(stderr, "[rg_knn] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
         t_start = now;
     };
-    Scratch sc;
+    DeviceScratch &sc = device_scratch(dev);
+    std::lock_guard<std::mutex> scratch_lock(sc.mu);
     __half *b16 = nullptr, *q16 = nullptr, *b16t = nullptr, *q16t = nullptr;
     float *bnorm = nullptr, *thr = nullptr;
     uint32_t *scal = nullptr, *cand_count = nullptr, *overflow = nullptr, *need_exact = nullptr, *flag_list = nullptr;
     uint64_t *cand = nullptr;
-    RG_CUDA_OK(sc.alloc(&b16, uint64_t(n_full) * b_rows_pad * kSlabK));
-    RG_CUDA_OK(sc.alloc(&q16, uint64_t(n_full) * q_rows_pad * kSlabK));
-    RG_CUDA_OK(sc.alloc(&b16t, b_rows_pad * std::max<uint32_t>(tail_k, 16)));
-    RG_CUDA_OK(sc.alloc(&q16t, q_rows_pad * std::max<uint32_t>(tail_k, 16)));
-    RG_CUDA_OK(sc.alloc(&bnorm, n));
-    RG_CUDA_OK(sc.alloc(&thr, q_batch));
-    RG_CUDA_OK(sc.alloc(&scal, 8));
-    RG_CUDA_OK(sc.alloc(&cand_count, q_batch));
-    RG_CUDA_OK(sc.alloc(&overflow, q_batch));
-    RG_CUDA_OK(sc.alloc(&need_exact, q_batch));
-    RG_CUDA_OK(sc.alloc(&flag_list, q_batch));
-    RG_CUDA_OK(sc.alloc(&cand, q_batch * kCap));
+    RG_CUDA_OK(sc.get(0, &b16, uint64_t(n_full) * b_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.get(1, &q16, uint64_t(n_full) * q_rows_pad * kSlabK));
+    RG_CUDA_OK(sc.get(2, &b16t, b_rows_pad * std::max<uint32_t>(tail_k, 16)));
+    RG_CUDA_OK(sc.get(3, &q16t, q_rows_pad * std::max<uint32_t>(tail_k, 16)));
+    RG_CUDA_OK(sc.get(4, &bnorm, n));
+    RG_CUDA_OK(sc.get(5, &thr, q_batch));
+    RG_CUDA_OK(sc.get(6, &scal, 8));
+    RG_CUDA_OK(sc.get(7, &cand_count, q_batch));
+    RG_CUDA_OK(sc.get(8, &overflow, q_batch));
+    RG_CUDA_OK(sc.get(9, &need_exact, q_batch));
+    RG_CUDA_OK(sc.get(10, &flag_list, nq));
+    RG_CUDA_OK(sc.get(11, &cand, q_batch * kCap));
 
-    lap("scratch allocation");
-    // scal[0] = max|b| bits, scal[1] = max |b|^2 bits, scal[2] = max|q| bits, scal[3] = #flagged
+    lap("scratch");
+    // scal[0] = max|b| bits, scal[1] = max |b|^2 bits, scal[2] = max|q| bits, scal[3] / scal[4] = #flagged (pass 1 / pass 2)
+    const bool have_base = reuse_base && sc.prep_base == d_base && sc.prep_n == n && sc.prep_dim == dim;
+    sc.prep_base = nullptr;  // invalid while the buffers are being rewritten
     RG_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
-    absmax_kernel<<<sms * 8, 256, 0, st>>>(d_base, n * dim, scal + 0);
+    if (!have_base) absmax_kernel<<<sms * 8, 256, 0, st>>>(d_base, n * dim, scal + 0);
     absmax_kernel<<<sms * 8, 256, 0, st>>>(d_queries, nq * dim, scal + 2);
     uint32_t h_scal[8];
     RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
     RG_CUDA_OK(cudaStreamSynchronize(st));
-    float max_b, max_q;
+    float max_b, max_q, max_bnorm2;
     memcpy(&max_b, &h_scal[0], 4);
     memcpy(&max_q, &h_scal[2], 4);
-    const float scale_b = pow2_scale(max_b), scale_q = pow2_scale(max_q);
-    to_half_slabs_kernel<<<sms * 8, 256, 0, st>>>(d_base, n, dim, b_rows_pad, n_full, tail_k, scale_b, b16, b16t, bnorm, scal + 1);
-    RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
-    RG_CUDA_OK(cudaStreamSynchronize(st));
-    float max_bnorm2;
-    memcpy(&max_bnorm2, &h_scal[1], 4);
+    const float scale_b = have_base ? sc.prep_scale : pow2_scale(max_b), scale_q = pow2_scale(max_q);
+    if (have_base) {
+        max_bnorm2 = sc.prep_max_bnorm2;
+    } else {
+        to_half_slabs_kernel<<<sms * 8, 256, 0, st>>>(d_base, n, dim, b_rows_pad, n_full, tail_k, scale_b, b16, b16t, bnorm, scal + 1);
+        RG_CUDA_OK(cudaMemcpyAsync(h_scal, scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        memcpy(&max_bnorm2, &h_scal[1], 4);
+    }
+    sc.prep_base = d_base;
+    sc.prep_n = n;
+    sc.prep_dim = dim;
+    sc.prep_scale = scale_b;
+    sc.prep_max_bnorm2 = max_bnorm2;
     // FP16 rounding: |fl(x) - x| <= 2^-11 |x| per operand -> |<q,b>~ - <q,b>| <= (2^-10 + 2^-22) |q| |b|; 2% slack
     // covers FP32 accumulation; L2 scores carry the factor 2 of -2<q,b>.
     const float eps_factor = 1.02f * std::ldexp(1.f, -10) * std::sqrt(max_bnorm2) * (ip ? 1.f : 2.f);
@@ -1054,7 +1185,6 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     uint32_t n_stages = uint32_t((size_t(smem_max) - misc - size_t(a_bufs) * a_bytes) / kSlabBytes);
     n_stages = std::min<uint32_t>(n_stages, 16);
     const size_t gemm_smem = size_t(a_bufs) * a_bytes + size_t(n_stages) * kSlabBytes + misc;
-    (void)nslab;
     RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem)));
@@ -1099,113 +1229,147 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     const size_t scan_smem = (8 * 256 + 1024) * 8;
     RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
     RG_CUDA_OK(cudaFuncSetAttribute(knn_exact_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
-
     lap("tensor maps + attributes");
-    uint64_t launches = 5, flagged_total = 0;
-    for (uint64_t q0 = 0; q0 < nq; q0 += q_batch) {
-        const uint32_t bq = uint32_t(std::min<uint64_t>(q_batch, nq - q0));
-        const float *dq = d_queries + q0 * dim;
-        to_half_slabs_kernel<<<sms * 4, 256, 0, st>>>(dq, bq, dim, q_rows_pad, n_full, tail_k, scale_q, q16, q16t, nullptr, nullptr);
-        fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
-        RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
-        RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
-        launches += 2;
-        GemmParams gp;
-        memset(&gp, 0, sizeof(gp));
-        gp.n_full = n_full;
-        gp.tail_k = tail_k;
-        gp.a_bytes = a_bytes;
-        gp.a_bufs = a_bufs;
-        gp.nq = bq;
-        gp.m_tiles = (bq + 2 * kTileM - 1) / (2 * kTileM);
-        gp.chunk_tiles = kChunkTiles;
-        gp.q_rows_pad = q_rows_pad;
-        gp.b_rows_pad = b_rows_pad;
-        gp.n_valid = n;
-        gp.id_base = id_base;
-        gp.l2 = ip ? 0 : 1;
-        gp.inv_scale = 1.f / (scale_q * scale_b);
-        gp.bnorm = bnorm;
-        gp.thr = thr;
-        gp.cand = cand;
-        gp.cand_count = cand_count;
-        gp.n_stages = n_stages;
-        // blocks of doubling size: [0,1024), [1024,2048), [2048,4096), ...  (tau = +inf in the first one: every score
-        // of the first 1024 rows is kept, so the list can never overflow there)
-        // RG_KNN_GROWTH = g (2..8, default 2): a block is (g-1) x everything seen so far, i.e. ~(g-1) k' expected hits per query
-        static const uint64_t growth = [] {
-            const char *e = getenv("RG_KNN_GROWTH");
-            const long g = e ? atol(e) : 2;
-            return uint64_t(g < 2 ? 2 : (g > 8 ? 8 : g));
-        }();
-        // RG_KNN_DENSE_ROWS: blocks that start before this many rows use the dense-hit epilogue (default 4096 = the first
-        // three blocks; measured per block at 10M x 32768, profiles/r01_launches_knn_*)
-        static const uint64_t dense_rows = [] {
-            const char *e = getenv("RG_KNN_DENSE_ROWS");
-            return uint64_t(e ? atoll(e) : 4096);
-        }();
-        uint64_t lo = 0, len = kCap;
-        while (lo < b_rows_pad) {
-            const uint64_t hi = std::min(b_rows_pad, lo + len);
-            gp.row_lo = lo;
-            gp.n_tiles = uint32_t((hi - lo) / kPairN);
-            const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
-            const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
-            // the threshold after `lo` rows lets ~k' / lo of the scores through: dense handling only while that is percents
-            const bool dense = lo < dense_rows;
-            if (ip) {
-                if (dense) knn_gemm_filter_kernel<false, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-                else knn_gemm_filter_kernel<false, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-            } else {
-                if (dense) knn_gemm_filter_kernel<true, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-                else knn_gemm_filter_kernel<true, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
-            }
-            knn_select_kernel<<<(bq + 3) / 4, 128, 0, st>>>(cand, cand_count, thr, overflow, bq, kprime);
+
+    // RG_KNN_GROWTH = g (2..8): a block is (g-1) x everything seen so far.  RG_KNN_DENSE_ROWS: blocks that start before this
+    // many rows use the dense-hit epilogue (measured per block at 10M x 32768, profiles/r01_launches_knn_*)
+    const uint64_t growth_opt = env_u64("RG_KNN_GROWTH", 0, 0, 8);
+    const uint64_t dense_rows = env_u64("RG_KNN_DENSE_ROWS", 4096, 0, 1ull << 40);
+    uint64_t launches = 5;
+
+    // One pass over `pq` [pnq][dim] (device): results to out.ids/out.dists [pnq][K]; queries without a certificate are
+    // appended to out.flag_list.  No host synchronisation inside.
+    auto run_pass = [&](const float *pq, uint64_t pnq, bool opt, const PassOutput &out) -> rg_status {
+        const uint64_t growth = growth_opt >= 2 ? growth_opt : (opt ? 4 : 2);
+        for (uint64_t q0 = 0; q0 < pnq; q0 += q_batch) {
+            const uint32_t bq = uint32_t(std::min<uint64_t>(q_batch, pnq - q0));
+            const float *dq = pq + q0 * dim;
+            to_half_slabs_kernel<<<sms * 4, 256, 0, st>>>(dq, bq, dim, q_rows_pad, n_full, tail_k, scale_q, q16, q16t, nullptr, nullptr);
+            fill_f32_kernel<<<64, 256, 0, st>>>(thr, bq, INFINITY);
+            RG_CUDA_OK(cudaMemsetAsync(cand_count, 0, bq * sizeof(uint32_t), st));
+            RG_CUDA_OK(cudaMemsetAsync(overflow, 0, bq * sizeof(uint32_t), st));
             launches += 2;
-            lo = hi;
-            len = std::max<uint64_t>(len, lo * (growth - 1));  // default: next block as large as everything seen so far
-        }
-        lap("  batch: gemm + select");
-        if (ip)
-            knn_rerank_kernel<true><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
-                                                                       eps_factor, max_bnorm2, bq, K, kprime, n, d_ids + q0 * K,
-                                                                       d_dists + q0 * K, need_exact);
-        else
-            knn_rerank_kernel<false><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
-                                                                        eps_factor, max_bnorm2, bq, K, kprime, n, d_ids + q0 * K,
-                                                                        d_dists + q0 * K, need_exact);
-        RG_CUDA_OK(cudaMemsetAsync(scal + 3, 0, sizeof(uint32_t), st));
-        compact_flags_kernel<<<(bq + 255) / 256, 256, 0, st>>>(need_exact, bq, flag_list, scal + 3);
-        uint32_t n_flagged = 0;
-        RG_CUDA_OK(cudaMemcpyAsync(&n_flagged, scal + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        RG_CUDA_OK(cudaStreamSynchronize(st));
-        launches += 2;
-        if (n_flagged) {
-            flagged_total += n_flagged;
-            const uint32_t grid = std::min<uint32_t>(n_flagged, uint32_t(sms) * 2);
+            GemmParams gp;
+            memset(&gp, 0, sizeof(gp));
+            gp.n_full = n_full;
+            gp.tail_k = tail_k;
+            gp.a_bytes = a_bytes;
+            gp.a_bufs = a_bufs;
+            gp.nq = bq;
+            gp.m_tiles = (bq + 2 * kTileM - 1) / (2 * kTileM);
+            gp.chunk_tiles = kChunkTiles;
+            gp.q_rows_pad = q_rows_pad;
+            gp.b_rows_pad = b_rows_pad;
+            gp.n_valid = n;
+            gp.id_base = id_base;
+            gp.l2 = ip ? 0 : 1;
+            gp.inv_scale = 1.f / (scale_q * scale_b);
+            gp.bnorm = bnorm;
+            gp.thr = thr;
+            gp.cand = cand;
+            gp.cand_count = cand_count;
+            gp.n_stages = n_stages;
+            // blocks [0,1024), then (growth-1) x everything seen so far (tau = +inf in the first block: every score of the
+            // first 1024 rows is kept, so the list can never overflow there)
+            uint64_t lo = 0, len = kCap;
+            while (lo < b_rows_pad) {
+                const uint64_t hi = std::min(b_rows_pad, lo + len);
+                gp.row_lo = lo;
+                gp.n_tiles = uint32_t((hi - lo) / kPairN);
+                const uint32_t units = ((gp.n_tiles + kChunkTiles - 1) / kChunkTiles) * gp.m_tiles;
+                const uint32_t grid = 2 * std::min<uint32_t>(units, max_pairs);
+                // the threshold after `lo` rows lets ~r / lo of the scores through: dense handling only while that is percents
+                const bool dense = lo < dense_rows;
+                if (ip) {
+                    if (dense) knn_gemm_filter_kernel<false, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                    else knn_gemm_filter_kernel<false, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                } else {
+                    if (dense) knn_gemm_filter_kernel<true, true><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                    else knn_gemm_filter_kernel<true, false><<<grid, kThreads, gemm_smem, st>>>(map_q, map_qt, map_b, map_bt, gp);
+                }
+                // rank of the new threshold among the scores kept so far (see "Threshold schedule" above); the last
+                // block always ends with the conservative k' so that K3 re-scores k' survivors, not c k'
+                uint32_t rank = kprime;
+                if (opt && hi < b_rows_pad) {
+                    const uint64_t seen = std::min<uint64_t>(hi, n);
+                    const uint64_t est = (c_safety * kprime * seen + n - 1) / n;
+                    rank = uint32_t(std::min<uint64_t>(kprime, std::max<uint64_t>(r_min, est)));
+                }
+                knn_select_kernel<<<(bq + 3) / 4, 128, 0, st>>>(cand, cand_count, thr, overflow, bq, rank);
+                launches += 2;
+                lo = hi;
+                len = std::max<uint64_t>(len, lo * (growth - 1));
+            }
+            lap("  batch: gemm + select");
             if (ip)
-                knn_exact_scan_kernel<true><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, dq, dim, flag_list, n_flagged, K,
-                                                                          d_ids + q0 * K, d_dists + q0 * K);
+                knn_rerank_kernel<true><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
+                                                                           eps_factor, max_bnorm2, bq, K, n, out.ids + q0 * K,
+                                                                           out.dists + q0 * K, need_exact);
             else
-                knn_exact_scan_kernel<false><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, dq, dim, flag_list, n_flagged, K,
-                                                                           d_ids + q0 * K, d_dists + q0 * K);
-            launches += 1;
+                knn_rerank_kernel<false><<<(bq + 3) / 4, 128, 4 * kCap * 8, st>>>(d_base, dq, dim, id_base, cand, cand_count, thr, overflow,
+                                                                            eps_factor, max_bnorm2, bq, K, n, out.ids + q0 * K,
+                                                                            out.dists + q0 * K, need_exact);
+            append_flags_kernel<<<(bq + 255) / 256, 256, 0, st>>>(need_exact, bq, uint32_t(q0), out.flag_list, out.flag_count);
+            launches += 2;
+            RG_CUDA_OK(cudaGetLastError());
+            lap("  batch: rerank");
         }
-        RG_CUDA_OK(cudaGetLastError());
-        lap("  batch: rerank + exact scan");
+        return RG_OK;
+    };
+    auto read_count = [&](const uint32_t *d_count, uint32_t *h) -> rg_status {
+        RG_CUDA_OK(cudaMemcpyAsync(h, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        return RG_OK;
+    };
+    auto exact_scan = [&](const float *pq, const uint32_t *list, uint32_t count, uint32_t *ids, float *dists) {
+        const uint32_t grid = std::min<uint32_t>(count, uint32_t(sms) * 2);
+        if (ip) knn_exact_scan_kernel<true><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, pq, dim, list, count, K, ids, dists);
+        else knn_exact_scan_kernel<false><<<grid, 256, scan_smem, st>>>(d_base, n, id_base, pq, dim, list, count, K, ids, dists);
+        launches += 1;
+    };
+
+    uint64_t redo_total = 0, scan_total = 0;
+    PassOutput main_out = {d_ids, d_dists, flag_list, scal + 3};
+    if ((s = run_pass(d_queries, nq, optimistic, main_out)) != RG_OK) return s;
+    uint32_t n_flagged = 0;
+    if ((s = read_count(scal + 3, &n_flagged)) != RG_OK) return s;  // the only synchronisation after the set-up
+    if (n_flagged && !optimistic) {
+        scan_total = n_flagged;
+        exact_scan(d_queries, flag_list, n_flagged, d_ids, d_dists);
+    } else if (n_flagged) {
+        // second pass, conservative schedule, over the gathered flagged queries; its own failures take the exact scan
+        redo_total = n_flagged;
+        float *rq = nullptr, *rd = nullptr;
+        uint32_t *ri = nullptr, *rflag = nullptr;
+        RG_CUDA_OK(sc.get(12, &rq, uint64_t(n_flagged) * dim));
+        RG_CUDA_OK(sc.get(13, &ri, uint64_t(n_flagged) * K));
+        RG_CUDA_OK(sc.get(14, &rd, uint64_t(n_flagged) * K));
+        RG_CUDA_OK(sc.get(15, &rflag, n_flagged));
+        gather_rows_kernel<<<sms * 4, 256, 0, st>>>(d_queries, flag_list, n_flagged, dim, rq);
+        PassOutput redo_out = {ri, rd, rflag, scal + 4};
+        if ((s = run_pass(rq, n_flagged, false, redo_out)) != RG_OK) return s;
+        uint32_t n_scan = 0;
+        if ((s = read_count(scal + 4, &n_scan)) != RG_OK) return s;
+        if (n_scan) {
+            scan_total = n_scan;
+            exact_scan(rq, rflag, n_scan, ri, rd);
+        }
+        scatter_results_kernel<<<sms * 4, 256, 0, st>>>(ri, rd, flag_list, n_flagged, K, d_ids, d_dists);
+        launches += 2;
     }
+    RG_CUDA_OK(cudaGetLastError());
     RG_CUDA_OK(cudaStreamSynchronize(st));
+    lap("redo + exact scan");
     if (stats) {
         stats[0] = launches;
-        stats[1] = flagged_total;
+        stats[1] = scan_total;
+        stats[2] = redo_total;
     }
     return RG_OK;
 }
 
 }  // namespace knn
 }  // namespace rg
-
-static thread_local uint64_t g_knn_stats[2] = {0, 0};  // per calling thread (one host thread per GPU in the tools)
 
 extern "C" {
 
@@ -1216,7 +1380,7 @@ rg_status rg_knn_exact_device(const float *d_base, uint64_t n, uint64_t id_base,
     rg::DeviceGuard guard(device);
     if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     return rg::knn::knn_device(d_base, n, id_base, d_queries, nq, dim, metric, K, d_ids, d_dists,
-                               static_cast<cudaStream_t>(cuda_stream), g_knn_stats);
+                               static_cast<cudaStream_t>(cuda_stream), g_knn_stats, false);
 }
 
 rg_status rg_knn_exact(const float *base, uint64_t n, uint64_t id_base, const float *queries, uint64_t nq, uint32_t dim,
@@ -1234,7 +1398,7 @@ rg_status rg_knn_exact(const float *base, uint64_t n, uint64_t id_base, const fl
     RG_CUDA_OK(sc.alloc(&d_d, nq * K));
     RG_CUDA_OK(cudaMemcpy(d_base, base, n * dim * sizeof(float), cudaMemcpyHostToDevice));
     RG_CUDA_OK(cudaMemcpy(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice));
-    rg_status s = rg::knn::knn_device(d_base, n, id_base, d_q, nq, dim, metric, K, d_i, d_d, nullptr, g_knn_stats);
+    rg_status s = rg::knn::knn_device(d_base, n, id_base, d_q, nq, dim, metric, K, d_i, d_d, nullptr, g_knn_stats, false);
     if (s != RG_OK) return s;
     RG_CUDA_OK(cudaMemcpy(ids, d_i, nq * K * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     RG_CUDA_OK(cudaMemcpy(dists, d_d, nq * K * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1283,5 +1447,20 @@ rg_status rg_knn_merge(const uint32_t *part_ids, const float *part_dists, uint32
 void rg_knn_last_stats(uint64_t *launches, uint64_t *exact_scans) {
     if (launches) *launches = g_knn_stats[0];
     if (exact_scans) *exact_scans = g_knn_stats[1];
+}
+uint64_t rg_knn_last_second_pass_count(void) { return g_knn_stats[2]; }
+
+rg_status rg_knn_release_scratch(int device) {
+    if (device >= 0) {
+        rg::DeviceGuard guard(device);
+        rg::knn::release_scratch(device);
+        return RG_OK;
+    }
+    const int n = rg_device_count();
+    for (int d = 0; d < n; ++d) {
+        rg::DeviceGuard guard(d);
+        rg::knn::release_scratch(d);
+    }
+    return RG_OK;
 }
 }

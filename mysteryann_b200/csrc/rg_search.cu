@@ -5,16 +5,21 @@
 // One CTA of W warps (W = 1..8, default 2) owns one query at a time; a persistent grid pulls query indices from an
 // atomic counter (the reference's schedule(dynamic,1)).  Per hop the CTA
 //   1. takes the closest unexpanded pool entry             (NeighborPriorityQueue::closest_unexpanded)
-//   2. reads that node's fixed-stride adjacency row, one word per thread (neighbour j belongs to warp j % W)
-//   3. filters the neighbours through an exact visited set (32-bit open-addressing hash, atomicCAS; by default an
-//      L2-resident slab per CTA in global memory, optionally shared memory; replaces VisitedList's uint16 tag array)
-//   4. every warp gathers the rows of ITS surviving neighbours HBM -> shared memory (TMA bulk copies on an mbarrier,
-//      or cp.async) in batches of `stage_rows`
+//   2. reads that node's fixed-stride adjacency row, one word per thread (neighbour j belongs to warp j % W); the row of
+//      the entry that will most likely be expanded NEXT is read in the same round trip: its visited-hash slots are
+//      prefetched into L2 and, when the speculation holds, its words are already in registers one hop later
+//   3. filters the neighbours through an exact visited set (open-addressing hash, atomicCAS; by default a slab per CTA
+//      in global memory - 16-bit quotient entries when the id range allows, else 32-bit keys - optionally shared
+//      memory; replaces VisitedList's uint16 tag array)
+//   4. every warp gathers the rows of ITS surviving neighbours HBM -> shared memory (TMA bulk copies on mbarriers, two
+//      staging buffers per warp so that batch b+1 is in flight while batch b is scored; or cp.async)
 //   5. and scores them 8 rows at a time, 4 lanes per row, in the exact FP32 operation order of the compiled
 //      reference distance (16 lane accumulators, unfused main loop, fused tails; distance.h:39-89,179-223);
 //      keys that cannot enter the pool (>= its last entry once full) are dropped on the spot
-//   6. all threads merge the hop's candidates into the sorted pool in parallel (rank by counting + binary search,
-//      scatter into the second pool buffer) - same final state as NeighborPriorityQueue::insert one by one.
+//   6. all threads merge the hop's candidates into the sorted pool IN PLACE: candidates are ranked against the pool
+//      (binary search) and against each other, pool entries behind the first insertion point shift right by the number
+//      of candidates in front of them (binary search in the sorted candidates), top-down in chunks of one entry per
+//      thread - O((L + C) log C / T) per thread, same final state as NeighborPriorityQueue::insert one by one.
 // Within a hop the order of insertion does not change the final pool (bounded sorted set under the strict order
 // (distance,id)), so steps 2-6 are batch operations with bit-identical results, cmps and hops included.
 #include <algorithm>
@@ -30,8 +35,14 @@ namespace rg {
 enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4 };
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kMaxWarps = 8;
+#ifndef RG_K1_MIN_CTAS
+#define RG_K1_MIN_CTAS 3  // 256-thread CTAs per SM the register allocation must allow: caps K1 at 80 registers per thread
+                          // (64 costs 4-6 % at L_pq = 55, 128 loses a third of the resident queries: profiles/r02_k1_ab_*.txt)
+#endif
 // shared control words
-enum { kCtlWork = 0, kCtlNvis = 1, kCtlHop0 = 4 /* 2 x {ncand, ndup, minpos, curpos} */ };
+enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */ };
+// visited-set flavours
+enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2 };
 
 struct SearchParams {
     const float *base;
@@ -43,102 +54,158 @@ struct SearchParams {
     uint32_t *hops;
     uint32_t *counters;
     uint32_t *overflow_list;   // primary pass appends here; fallback pass reads from here
-    uint32_t *ghash;           // global visited-hash slabs, one per CTA (kGlobalHash only)
+    uint32_t *ghash;           // global visited-hash slabs, one per CTA (global flavours only)
     uint32_t nq;               // primary: number of queries; fallback: unused (count read from counters)
     uint32_t dim, adj_stride, ep, k, L;
     uint32_t hash_log2, hash_limit;
+    // 16-bit quotient entries (kHashGlobal16): x = (id * h16_mult) mod 2^h16_bits is a bijection of the id range; the home
+    // slot is its top hash_log2 bits, the entry stores the remaining h16_rbits bits and the probe displacement
+    uint32_t h16_bits, h16_rbits, h16_dbits, h16_maxd, h16_mult;
     uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
+    uint32_t stage_bufs;       // staging buffers per warp (1, or 2: the next batch is in flight while one is scored)
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
     uint32_t fallback;         // 1 = second pass over overflow_list with the big global table
     uint32_t l2_hint;          // bit 0: base-row gathers evict_first (bit 1, host side: visited-hash slabs persist in L2)
-    uint32_t adj_prefetch;     // bit 0: L2-prefetch the adjacency row of the next unexpanded pool entry at selection
-                               // time; bit 1: of every scored candidate that beats it (it will be expanded first)
+    uint32_t adj_prefetch;     // bit 0: speculate on the next unexpanded pool entry (adjacency row read ahead, its hash
+                               // slots prefetched into L2); bit 1: L2-prefetch the adjacency row of every scored
+                               // candidate that beats it (it will be expanded first)
     // build mode (kBuild, SearchProjectionGraphInternal src/index_bipartite.cpp:1279-1350): query w is base row
     // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
     uint32_t node_lo, exp_cap;
     uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
-    uint32_t off_pool0, off_pool1, off_cand, off_rank, off_ctrl, off_hash, off_warp;
-    uint32_t warp_bytes, woff_cid, woff_stage;  // per-warp area: [mbarrier][candidate ids][row staging]
+    uint32_t off_pool, off_cand, off_sorted, off_pos, off_ctrl, off_hash, off_warp;
+    uint32_t warp_bytes, woff_cid, woff_stage, stage_bytes;  // per-warp area: [2 mbarriers][candidate ids][row staging x bufs]
 };
 
 // ---- exact visited set --------------------------------------------------------------------------
-__device__ __forceinline__ bool visited_test_and_set(uint32_t *table, uint32_t log2, uint32_t id) {
+// returns 1 = first visit, 0 = already visited, 2 = table cannot take the id (16-bit flavour: displacement field exhausted)
+__device__ __forceinline__ uint32_t visited_test_and_set32(uint32_t *table, uint32_t log2, uint32_t id) {
     const uint32_t mask = (1u << log2) - 1u;
     uint32_t slot = (id * 0x9E3779B1u) >> (32 - log2);
     for (;;) {
         uint32_t old = atomicCAS(table + slot, kEmpty, id);
-        if (old == kEmpty) return true;   // first visit
-        if (old == id) return false;      // already visited
+        if (old == kEmpty) return 1u;   // first visit
+        if (old == id) return 0u;       // already visited
         slot = (slot + 1) & mask;
     }
 }
+__device__ __forceinline__ uint32_t hash16_home(const SearchParams &p, uint32_t id, uint32_t *rem) {
+    const uint32_t x = (id * p.h16_mult) & ((1u << p.h16_bits) - 1u);
+    *rem = x & ((1u << p.h16_rbits) - 1u);
+    return x >> p.h16_rbits;
+}
+__device__ __forceinline__ uint32_t visited_test_and_set16(unsigned short *table, const SearchParams &p, uint32_t id) {
+    const uint32_t mask = (1u << p.hash_log2) - 1u;
+    uint32_t rem;
+    uint32_t slot = hash16_home(p, id, &rem);
+    const uint32_t hi = rem << p.h16_dbits;
+    for (uint32_t d = 0; d <= p.h16_maxd; ++d) {
+        const unsigned short want = (unsigned short)(hi | d);
+        const unsigned short old = atomicCAS(table + slot, (unsigned short)0xFFFFu, want);
+        if (old == 0xFFFFu) return 1u;
+        if (old == want) return 0u;     // same displacement -> same home slot, same remainder -> same id
+        slot = (slot + 1) & mask;
+    }
+    return 2u;
+}
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr)); }
+
+// first index in sorted keys[0..n) whose key (flag bit cleared) is >= key
+__device__ __forceinline__ uint32_t lower_bound_key(const uint64_t *keys, uint32_t n, uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((keys[mid] & ~1ull) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
 
 // kGather: 1 = cp.async (LDGSTS 16 B per lane), 2 = TMA bulk copy (one UBLKCP per row) on an mbarrier
-template <bool kIP, int kGather, bool kGlobalHash, bool kBuild>
-__global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchParams p) {
+template <bool kIP, int kGather, int kHash, bool kBuild>
+__global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, T = blockDim.x, W = T >> 5;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t grp = lane >> 2, t = lane & 3;
     float *s_query = reinterpret_cast<float *>(smem_raw);
-    uint64_t *s_pool0 = reinterpret_cast<uint64_t *>(smem_raw + p.off_pool0);
-    uint64_t *s_pool1 = reinterpret_cast<uint64_t *>(smem_raw + p.off_pool1);
+    uint64_t *P = reinterpret_cast<uint64_t *>(smem_raw + p.off_pool);
     uint64_t *s_cand = reinterpret_cast<uint64_t *>(smem_raw + p.off_cand);
-    uint32_t *s_rank = reinterpret_cast<uint32_t *>(smem_raw + p.off_rank);
+    uint64_t *s_sorted = reinterpret_cast<uint64_t *>(smem_raw + p.off_sorted);
+    uint32_t *s_pos = reinterpret_cast<uint32_t *>(smem_raw + p.off_pos);
     volatile uint32_t *s_ctrl = reinterpret_cast<volatile uint32_t *>(smem_raw + p.off_ctrl);
     uint32_t *s_ctrl_nv = reinterpret_cast<uint32_t *>(smem_raw + p.off_ctrl);
     unsigned char *wa = smem_raw + p.off_warp + size_t(warp) * p.warp_bytes;
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);  // [2]
     uint32_t *s_cid = reinterpret_cast<uint32_t *>(wa + p.woff_cid);
-    float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
-    uint32_t *hash = kGlobalHash ? p.ghash + (size_t(blockIdx.x) << p.hash_log2)
-                                 : reinterpret_cast<uint32_t *>(smem_raw + p.off_hash);
+    unsigned char *s_stage_raw = wa + p.woff_stage;
+    uint32_t *hash32 = kHash == kHashShared ? reinterpret_cast<uint32_t *>(smem_raw + p.off_hash)
+                                            : p.ghash + (size_t(blockIdx.x) << (kHash == kHashGlobal16 ? p.hash_log2 - 1 : p.hash_log2));
+    unsigned short *hash16 = reinterpret_cast<unsigned short *>(hash32);
 
     const uint32_t dim = p.dim, n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
     const uint32_t cpr = dim >> 2;  // 16-byte chunks per row
     const uint32_t L = p.L, BR = p.stage_rows, RS = p.row_stride;
-    uint32_t mb_phase = 0;
+    uint32_t mb_phase = 0;          // bit b = phase of this warp's mbarrier b
     const bool rows_evict_first = (p.l2_hint & 1u) != 0;
     const bool pf_next = (p.adj_prefetch & 1u) != 0, pf_cand = (p.adj_prefetch & 2u) != 0;
     const uint64_t pol_first = l2_policy_evict_first();
     const uint32_t adj_row_bytes = p.adj_stride * 4u;
+    const bool two_bufs = kGather == 2 && p.stage_bufs == 2;
 
     if (kGather == 2) {
         if (lane == 0) {
-            mbar_init(s_mbar, 1);
+            mbar_init(&s_mbar[0], 1);
+            mbar_init(&s_mbar[1], 1);
             fence_mbar_init();
         }
     }
     __syncthreads();
 
+    auto visit = [&](uint32_t id) -> uint32_t {
+        if (kHash == kHashGlobal16) return visited_test_and_set16(hash16, p, id);
+        return visited_test_and_set32(hash32, p.hash_log2, id);
+    };
+
     // Gathers and scores this warp's candidates s_cid[0..n); keys below `tail` are appended to the CTA-wide list.
     // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
     // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
     auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key) {
-        for (uint32_t c0 = 0; c0 < n; c0 += BR) {
-            const uint32_t rows = min(BR, n - c0);
+        const uint32_t nb = (n + BR - 1) / BR;
+        auto issue = [&](uint32_t b) {  // TMA: batch b -> staging buffer b & 1 (or 0), completion on that buffer's mbarrier
+            const uint32_t buf = two_bufs ? (b & 1u) : 0u;
+            const uint32_t c0 = b * BR, rows = min(BR, n - c0);
+            float *stage = reinterpret_cast<float *>(s_stage_raw + size_t(buf) * p.stage_bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&s_mbar[buf], rows * dim * 4u);
+            __syncwarp();
+            if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
+                for (uint32_t r = lane; r < rows; r += 32)
+                    bulk_g2s_hint(stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, &s_mbar[buf], pol_first);
+            } else {
+                for (uint32_t r = lane; r < rows; r += 32)
+                    bulk_g2s(stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, &s_mbar[buf]);
+            }
+        };
+        if (kGather == 2 && nb) issue(0);
+        for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t c0 = b * BR, rows = min(BR, n - c0);
+            const uint32_t buf = two_bufs ? (b & 1u) : 0u;
+            const float *stage = reinterpret_cast<const float *>(s_stage_raw + size_t(buf) * p.stage_bytes);
             if (kGather == 2) {
-                if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
-                __syncwarp();
-                if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
-                    for (uint32_t r = lane; r < rows; r += 32)
-                        bulk_g2s_hint(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar, pol_first);
-                } else {
-                    for (uint32_t r = lane; r < rows; r += 32)
-                        bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
-                }
-                mbar_wait(s_mbar, mb_phase);
-                mb_phase ^= 1u;
+                if (two_bufs && b + 1 < nb) issue(b + 1);  // the other buffer was released by the __syncwarp of batch b-1
+                mbar_wait(&s_mbar[buf], (mb_phase >> buf) & 1u);
+                mb_phase ^= 1u << buf;
             } else {
                 const uint32_t total = rows * cpr;
+                float *st = const_cast<float *>(stage);
                 for (uint32_t idx = lane; idx < total; idx += 32) {
                     const uint32_t r = __umulhi(idx, p.chunk_magic);
                     const uint32_t c = idx - r * cpr;
-                    cp_async16(s_stage + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
+                    cp_async16(st + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -148,7 +215,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 const uint32_t r = r0 + grp;
                 const bool valid = r < rows;
                 const uint32_t rr = valid ? r : rows - 1;
-                const float4 *rp = reinterpret_cast<const float4 *>(s_stage + size_t(rr) * RS) + t;
+                const float4 *rp = reinterpret_cast<const float4 *>(stage + size_t(rr) * RS) + t;
                 const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
                 const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
                 const uint64_t key = make_key(d, s_cid[c0 + rr]);
@@ -165,7 +232,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                     if (keep) s_cand[pos0 + __popc(m & lanemask_lt())] = key;
                 }
             }
-            __syncwarp();  // all reads of the staging buffer done before the next batch lands in it
+            __syncwarp();  // all reads of this staging buffer done before another batch lands in it
+            if (kGather == 2 && !two_bufs && b + 1 < nb) issue(b + 1);
         }
     };
 
@@ -174,9 +242,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         if (tid == 0) {
             s_ctrl[kCtlWork] = atomicAdd(&p.counters[p.fallback ? kCntWork2 : kCntWork], 1u);
             s_ctrl[kCtlNvis] = 0;
+            s_ctrl[kCtlHashFull] = 0;
             s_ctrl[kCtlHop0 + 0] = 0;  // ncand
             s_ctrl[kCtlHop0 + 1] = 0;  // ndup
-            s_ctrl[kCtlHop0 + 2] = L;  // minpos
+            s_ctrl[kCtlHop0 + 2] = L;  // minlo
             s_ctrl[kCtlHop0 + 3] = L;  // curpos
             s_ctrl[kCtlHop0 + 4] = 0;
             s_ctrl[kCtlHop0 + 5] = 0;
@@ -194,16 +263,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                                                                         : p.queries + size_t(qi) * dim);
             float4 *dst = reinterpret_cast<float4 *>(s_query);
             for (uint32_t i = tid; i < cpr; i += T) dst[i] = src[i];
-            uint4 *h4 = reinterpret_cast<uint4 *>(hash);
+            uint4 *h4 = reinterpret_cast<uint4 *>(hash32);
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            for (uint32_t i = tid; i < (1u << (p.hash_log2 - 2)); i += T) h4[i] = e4;
+            const uint32_t n_vec = 1u << (p.hash_log2 - (kHash == kHashGlobal16 ? 3 : 2));
+            for (uint32_t i = tid; i < n_vec; i += T) h4[i] = e4;
         }
         __syncthreads();
 
         uint32_t size = 0, cur = 0, hops = 0, nvis = 0, hp = 0;  // hp: parity of the hop's control words
         uint64_t tail = ~0ull;  // (distance,id) of the last entry once the pool is full, else +inf
-        uint64_t *P = s_pool0, *N = s_pool1;
         bool have_cur = false, overflow = false;
+        // speculation: adjacency words of the node expected to be expanded next (see step 2 above)
+        uint32_t spec_id = kEmpty, spec_deg = 0, sreg[3] = {kEmpty, kEmpty, kEmpty};
 
         // entry point: scored and inserted, NOT marked visited (src/index_bipartite.cpp:2337-2353); the build-time
         // search does mark it (:1309)
@@ -211,7 +282,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
         if (warp == 0) {
             if (lane == 0) {
                 s_cid[0] = p.ep;
-                if (kBuild) visited_test_and_set(hash, p.hash_log2, p.ep);
+                if (kBuild) visit(p.ep);
             }
             __syncwarp();
             gather_and_score(1, tail, kCtlHop0, ~0ull);
@@ -222,6 +293,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
             const uint32_t ctl = kCtlHop0 + 4 * hp, octl = kCtlHop0 + 4 * (hp ^ 1u);  // this hop's / the other hop's words
             const uint32_t C = s_ctrl[ctl + 0];
             nvis = s_ctrl[kCtlNvis];
+            if (kHash == kHashGlobal16 && s_ctrl[kCtlHashFull]) {  // a displacement field ran out: big-table pass
+                overflow = true;
+                break;
+            }
             uint32_t start;
             if (C == 0) {
                 // nothing to insert: flag the expanded entry (closest_unexpanded, neighbor.h:185-192)
@@ -239,17 +314,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 //     re-scored entry point: "Make sure the same id isn't inserted into the set" (neighbor.h:161)
                 for (uint32_t j = tid; j < C; j += T) {
                     const uint64_t key = s_cand[j];
-                    uint32_t lo = 0, hi = size;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if ((P[mid] & ~1ull) < key) lo = mid + 1;
-                        else hi = mid;
-                    }
+                    const uint32_t lo = lower_bound_key(P, size, key);
                     if (lo < size && (P[lo] & ~1ull) == key) {
                         s_cand[j] = ~0ull;
                         atomicAdd(&s_ctrl_nv[ctl + 1], 1u);
                     } else {
-                        s_rank[j] = lo;
+                        atomicMin(&s_ctrl_nv[ctl + 2], lo);
                     }
                 }
                 if (tid == 0) {  // the other hop's control words are free again
@@ -259,39 +329,51 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                     s_ctrl[octl + 3] = L;
                 }
                 __syncthreads();
-                const uint32_t ndup = s_ctrl[ctl + 1];
-                // (b) candidates -> new pool
+                const uint32_t Cn = C - s_ctrl[ctl + 1];   // candidates that are really new
+                const uint32_t minlo = min(s_ctrl[ctl + 2], size);  // pool entries in front of it do not move
+                // (b) candidates sorted by counting; final position = #pool entries + #candidates in front
                 for (uint32_t j = tid; j < C; j += T) {
                     const uint64_t key = s_cand[j];
                     if (key == ~0ull) continue;
                     uint32_t r = 0;
                     for (uint32_t i = 0; i < C; ++i) r += (s_cand[i] < key) ? 1u : 0u;
-                    const uint32_t pos = s_rank[j] + r;
-                    if (pos < L) {
-                        N[pos] = key;
-                        atomicMin(&s_ctrl_nv[ctl + 2], pos);
-                    }
+                    s_sorted[r] = key;
+                    s_pos[r] = lower_bound_key(P, size, key) + r;
                 }
-                // (c) old entries shift right by the number of candidates in front of them
-                for (uint32_t i = tid; i < size; i += T) {
-                    uint64_t e = P[i];
-                    const uint64_t ek = e & ~1ull;
-                    uint32_t sh = 0;
-                    for (uint32_t j = 0; j < C; ++j) sh += (s_cand[j] < ek) ? 1u : 0u;
-                    const uint32_t pos = i + sh;
-                    if (have_cur && i == cur) {
-                        e |= 1ull;
-                        s_ctrl[ctl + 3] = pos;
-                    }
-                    if (pos < L) N[pos] = e;
+                if (have_cur && cur < minlo && tid == 0) {  // the expanded entry stays where it is
+                    P[cur] |= 1ull;
+                    s_ctrl[ctl + 3] = cur;
                 }
                 __syncthreads();
-                size = min(L, size + C - ndup);
-                uint64_t *tmp = P;
-                P = N;
-                N = tmp;
-                const uint32_t minpos = s_ctrl[ctl + 2], curpos = s_ctrl[ctl + 3];
-                start = have_cur ? min(minpos, curpos + 1) : 0u;
+                // (c) pool entries [minlo, size) shift right by the number of candidates in front of them, in place:
+                //     chunks of T entries from the top down; a chunk's new positions are >= its old ones, i.e. inside the
+                //     chunk itself (read before the barrier) or above it (already moved)
+                for (uint32_t hi = size; hi > minlo;) {
+                    const uint32_t lo_c = (hi - minlo > T) ? hi - T : minlo;
+                    const uint32_t i = lo_c + tid;
+                    const bool valid = i < hi;
+                    uint64_t e = 0;
+                    uint32_t pos = 0;
+                    if (valid) {
+                        e = P[i];
+                        pos = i + lower_bound_key(s_sorted, Cn, e & ~1ull);
+                        if (have_cur && i == cur) {
+                            e |= 1ull;
+                            s_ctrl[ctl + 3] = pos;
+                        }
+                    }
+                    __syncthreads();
+                    if (valid && pos < L) P[pos] = e;
+                    hi = lo_c;
+                }
+                for (uint32_t r = tid; r < Cn; r += T) {
+                    const uint32_t pos = s_pos[r];
+                    if (pos < L) P[pos] = s_sorted[r];
+                }
+                __syncthreads();
+                size = min(L, size + Cn);
+                const uint32_t curpos = s_ctrl[ctl + 3];
+                start = have_cur ? min(minlo, curpos + 1) : 0u;
             }
             hp ^= 1u;
             {   // first unexpanded entry at or after `start` (everything in front of it is expanded)
@@ -321,18 +403,26 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 break;
             }
             // adjacency row: neighbour j is handled by warp j % W, lane (j / W) % 32; the first three rounds are
-            // requested together with the degree word: one DRAM round trip
+            // requested together with the degree word: one DRAM round trip - or none at all when this node was the
+            // one read ahead during the previous hop
             const uint32_t *row = p.adj + size_t(cur_id) * p.adj_stride;
-            uint32_t wreg[3];
+            uint32_t wreg[3], deg;
+            if (spec_id == cur_id) {
 #pragma unroll
-            for (uint32_t it = 0; it < 3; ++it) {
-                const uint32_t j = (lane + 32 * it) * W + warp;
-                wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
+                for (uint32_t it = 0; it < 3; ++it) wreg[it] = sreg[it];
+                deg = spec_deg;
+            } else {
+#pragma unroll
+                for (uint32_t it = 0; it < 3; ++it) {
+                    const uint32_t j = (lane + 32 * it) * W + warp;
+                    wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
+                }
+                deg = __ldg(row);
             }
-            const uint32_t deg = __ldg(row);
             // speculation for the NEXT hop: the best unexpanded entry behind `cur` is expanded next unless a candidate of
-            // this hop beats it; request its adjacency row now (one bulk L2 prefetch per CTA)
+            // this hop beats it; read its adjacency row now (same round trip as the row above)
             uint64_t next_key = tail;
+            spec_id = kEmpty;
             if (pf_next || pf_cand) {
                 uint32_t c = cur + 1, nx = size;
                 while (c < size) {
@@ -347,8 +437,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 }
                 if (nx < size) {
                     next_key = P[nx] & ~1ull;
-                    if (pf_next && warp == W - 1 && lane == 0)
-                        bulk_prefetch_l2(p.adj + size_t(key_id(next_key)) * p.adj_stride, adj_row_bytes);
+                    if (pf_next) {
+                        spec_id = key_id(next_key);
+                        const uint32_t *nrow = p.adj + size_t(spec_id) * p.adj_stride;
+#pragma unroll
+                        for (uint32_t it = 0; it < 3; ++it) {
+                            const uint32_t j = (lane + 32 * it) * W + warp;
+                            sreg[it] = (j + 1 < p.adj_stride) ? __ldg(nrow + 1 + j) : kEmpty;
+                        }
+                        spec_deg = __ldg(nrow);
+                    }
                 }
             }
             uint32_t n_w = 0;
@@ -359,13 +457,34 @@ __global__ void __launch_bounds__(kMaxWarps * 32) rg_search_kernel(const SearchP
                 else if (it == 1) word = wreg[1];
                 else if (it == 2) word = wreg[2];
                 else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
-                bool fresh = false;
-                if (j < deg && !(kBuild && word == self)) fresh = visited_test_and_set(hash, p.hash_log2, word);
+                uint32_t v = 0;
+                if (j < deg && !(kBuild && word == self)) v = visit(word);
+                if (kHash == kHashGlobal16 && v == 2u) {
+                    s_ctrl[kCtlHashFull] = 1;
+                    v = 0;
+                }
+                const bool fresh = v == 1u;
                 const uint32_t m = __ballot_sync(0xffffffffu, fresh);
                 if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
                 n_w += __popc(m);
             }
             __syncwarp();
+            if (pf_next && spec_id != kEmpty && kHash != kHashShared) {
+                // pull the visited-hash slots the speculated node's neighbours map to into L2: one hop from now their
+                // atomicCAS probes are L2 hits instead of HBM round trips on the query's dependent chain
+#pragma unroll
+                for (uint32_t it = 0; it < 3; ++it) {
+                    const uint32_t j = (lane + 32 * it) * W + warp;
+                    if (j < spec_deg) {
+                        if (kHash == kHashGlobal16) {
+                            uint32_t rem;
+                            prefetch_l2(hash16 + hash16_home(p, sreg[it], &rem));
+                        } else {
+                            prefetch_l2(hash32 + ((sreg[it] * 0x9E3779B1u) >> (32 - p.hash_log2)));
+                        }
+                    }
+                }
+            }
             if (n_w) {
                 if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
                 // a re-scored entry point lands here too; the merge drops it as a duplicate (neighbor.h:161) or the tail
@@ -418,9 +537,9 @@ typedef void (*SearchKernel)(const SearchParams);
 
 struct Geometry {
     SearchParams p;
-    int warps, gather;
-    bool global_hash;
+    int warps, gather, hash_kind;
     size_t smem_bytes;
+    uint64_t slab_bytes;  // global visited-hash bytes per CTA (0: shared memory)
     SearchKernel fn;
     int ctas_per_sm;
 };
@@ -438,18 +557,26 @@ static uint32_t auto_hash_log2(uint32_t L, bool global_space) {
     return lg;
 }
 
-static SearchKernel pick_kernel(bool ip, int gather, bool gh, bool build) {
-    if (build) return ip ? rg_search_kernel<true, 2, true, true> : rg_search_kernel<false, 2, true, true>;
-    if (gather == 2) {
-        if (gh) return ip ? rg_search_kernel<true, 2, true, false> : rg_search_kernel<false, 2, true, false>;
-        return ip ? rg_search_kernel<true, 2, false, false> : rg_search_kernel<false, 2, false, false>;
-    }
-    if (gh) return ip ? rg_search_kernel<true, 1, true, false> : rg_search_kernel<false, 1, true, false>;
-    return ip ? rg_search_kernel<true, 1, false, false> : rg_search_kernel<false, 1, false, false>;
+template <bool kIP, int kGather, int kHash>
+static SearchKernel pick_build(bool build) {
+    if (build) return rg_search_kernel<kIP, 2, kHash == kHashShared ? kHashGlobal32 : kHash, true>;
+    return rg_search_kernel<kIP, kGather, kHash, false>;
+}
+template <bool kIP, int kGather>
+static SearchKernel pick_hash(int hash_kind, bool build) {
+    if (hash_kind == kHashGlobal16) return pick_build<kIP, kGather, kHashGlobal16>(build);
+    if (hash_kind == kHashGlobal32) return pick_build<kIP, kGather, kHashGlobal32>(build);
+    return pick_build<kIP, kGather, kHashShared>(build);
+}
+static SearchKernel pick_kernel(bool ip, int gather, int hash_kind, bool build) {
+    if (gather == 2 || build) return ip ? pick_hash<true, 2>(hash_kind, build) : pick_hash<false, 2>(hash_kind, build);
+    return ip ? pick_hash<true, 1>(hash_kind, build) : pick_hash<false, 1>(hash_kind, build);
 }
 
+static bool persisting_window_fits(const rg_index *ix, uint64_t bytes);
+
 static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g,
-                               int warps_override = 0) {
+                               int warps_override = 0, bool allow16 = true) {
     SearchParams &p = g->p;
     memset(&p, 0, sizeof(p));
     p.dim = ix->dim;
@@ -464,6 +591,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.row_stride = (ix->dim % 32 <= 16) ? ix->dim - ix->dim % 32 + 16 : ix->dim - ix->dim % 32 + 48;
     p.stage_rows = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
+    if (build) g->gather = 2;
+    p.stage_bufs = (g->gather == 2 && ix->cfg_stage_bufs == 2) ? 2u : 1u;
     g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
     if (warps_override) g->warps = warps_override;
     const uint32_t W = uint32_t(g->warps);
@@ -472,43 +601,61 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.fallback = fallback ? 1u : 0u;
     p.l2_hint = uint32_t(ix->cfg_l2_hint);
     p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
-    // visited set: an L2-resident slab per CTA in global memory unless shared memory was asked for (hash_space 1)
-    g->global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
+    // visited set: a slab per CTA in global memory (L2-resident at the usual beam widths) unless shared memory was asked
+    // for (hash_space 1).  Entries are 16-bit quotients when the id range leaves >= 6 bits for the probe displacement
+    // at a table no larger (in bytes) than the 32-bit one (hash_space 3 asks for them, 2 for 32-bit keys).
+    const bool global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
+    g->hash_kind = global_hash ? kHashGlobal32 : kHashShared;
+    if (global_hash && !fallback && ix->cfg_hash_space != 2 && allow16) {
+        uint32_t id_bits = 1;
+        while ((1ull << id_bits) < ix->n && id_bits < 32) ++id_bits;
+        const uint32_t h16 = std::max<uint32_t>(hl, id_bits > 10 ? id_bits - 10 : 0);  // >= 6 displacement bits
+        if (h16 <= hl + 1 && h16 <= 22) {
+            g->hash_kind = kHashGlobal16;
+            hl = h16;
+            p.h16_bits = std::max(id_bits, hl);
+            p.h16_rbits = p.h16_bits - hl;
+            p.h16_dbits = std::min<uint32_t>(16u - p.h16_rbits, 12u);
+            p.h16_maxd = (1u << p.h16_dbits) - 2u;
+            // odd multiplier ~ 2^bits / golden ratio: a bijection of [0, 2^bits) whose top bits mix well
+            p.h16_mult = (uint32_t(double(1ull << p.h16_bits) * 0.6180339887498949) | 1u) & uint32_t((1ull << p.h16_bits) - 1);
+        }
+    }
     p.hash_log2 = hl;
     p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
+    g->slab_bytes = g->hash_kind == kHashShared ? 0 : (uint64_t(g->hash_kind == kHashGlobal16 ? 2 : 4) << hl);
 
     uint32_t off = round_up(ix->dim * 4, 128);
-    p.off_pool0 = off;
-    off += round_up((L + 1) * 8, 128);
-    p.off_pool1 = off;
+    p.off_pool = off;
     off += round_up((L + 1) * 8, 128);
     p.off_cand = off;
     off += round_up(ix->adj_stride * 8, 128);
-    p.off_rank = off;
+    p.off_sorted = off;
+    off += round_up(ix->adj_stride * 8, 128);
+    p.off_pos = off;
     off += round_up(ix->adj_stride * 4, 128);
     p.off_ctrl = off;
     off += 128;
     p.off_hash = off;
-    if (!g->global_hash) off += (4u << hl);
+    if (g->hash_kind == kHashShared) off += (4u << hl);
     p.off_warp = off;
     const uint32_t cid_cap = round_up((ix->adj_stride - 1 + W - 1) / W, 8);
     p.woff_cid = 16;
     p.woff_stage = round_up(16 + cid_cap * 4, 128);
-    p.warp_bytes = p.woff_stage + round_up(p.stage_rows * p.row_stride * 4, 128);
+    p.stage_bytes = round_up(p.stage_rows * p.row_stride * 4, 128);
+    p.warp_bytes = p.woff_stage + p.stage_bufs * p.stage_bytes;
     off += W * p.warp_bytes;
     g->smem_bytes = off;
     if (size_t(off) > size_t(ix->max_smem_optin))
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "L_pq=%u needs %u bytes of shared memory per query (max %d)", L, off,
                         ix->max_smem_optin);
-    if (build) g->gather = 2;
-    g->fn = pick_kernel(ix->metric != RG_METRIC_L2, g->gather, g->global_hash, build);
+    g->fn = pick_kernel(ix->metric != RG_METRIC_L2, g->gather, g->hash_kind, build);
     cudaError_t e = cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(g->smem_bytes));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, g->fn, g->warps * 32, g->smem_bytes);
     if (e != cudaSuccess) return rg::fail(RG_ERR_CUDA, "K1 launch configuration failed: %s", cudaGetErrorString(e));
     if (g->ctas_per_sm < 1) return rg::fail(RG_ERR_INTERNAL, "K1 does not fit on an SM (L_pq=%u)", L);
     if (ix->cfg_ctas) g->ctas_per_sm = std::min(g->ctas_per_sm, ix->cfg_ctas);
-    if (fallback) g->ctas_per_sm = std::min(g->ctas_per_sm, 4);  // big global tables: keep the slab count small
     return RG_OK;
 }
 
@@ -582,34 +729,53 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     if (nq == 0) return RG_OK;
 
     Geometry g1, g2;
-    rg_status s = make_geometry(ix, k, L, false, build, &g1);
+    rg_status s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
-    s = make_geometry(ix, k, L, true, build, &g2);
+    // Primary pass.  Automatic mode picks, in this order of preference (same-box A/B in profiles/r02_k1_ab_*.txt):
+    //   two warps per query, 32-bit hash keys    when the slabs of all resident queries fit the persisting part of L2
+    //   two warps per query, 16-bit quotients    when only the half-size slabs fit (the 16-bit CAS is a little slower
+    //                                            than the 32-bit one while both hit L2, but far faster than probing HBM)
+    //   four warps per query (half the residents), 32-bit then 16-bit, when that makes the slabs fit
+    //   two warps per query, 16-bit quotients    otherwise (nothing fits: at least halve the hash traffic)
+    const bool auto_hash = ix->cfg_hash_space == 0, auto_warps = ix->cfg_warps == 0;
+    auto fits = [&](const Geometry &g) {
+        const uint64_t cap = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g.ctas_per_sm);
+        return g.slab_bytes == 0 || persisting_window_fits(ix, cap * g.slab_bytes);
+    };
+    s = make_geometry(ix, k, L, false, build, &g1, 0, !auto_hash);
     if (s != RG_OK) return s;
-
-    // Warps per query, automatic mode: two warps per query keep the most queries resident, but from L_pq ~ 80 on their
-    // visited-hash slabs (64 KB each) no longer fit the persisting part of L2 together and the probes go to HBM.  Four
-    // warps per query halve the resident queries, so up to L_pq ~ 180 the slabs fit again: 0.74 -> 0.81 of the HBM peak
-    // at L_pq = 100 (profiles/r01_k1_large_L_variants.txt).  Beyond that nothing fits and two warps win again.
-    if (!build && ix->cfg_warps == 0 && g1.global_hash && (ix->cfg_l2_hint & 2)) {
-        const uint64_t cap2 = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm);
-        if (!persisting_window_fits(ix, (cap2 << g1.p.hash_log2) * sizeof(uint32_t))) {
-            Geometry g4;
-            if (make_geometry(ix, k, L, false, false, &g4, 4) == RG_OK && g4.global_hash) {
-                const uint64_t cap4 = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g4.ctas_per_sm);
-                if (persisting_window_fits(ix, (cap4 << g4.p.hash_log2) * sizeof(uint32_t))) g1 = g4;
+    if ((auto_hash || auto_warps) && (ix->cfg_l2_hint & 2) && !fits(g1)) {
+        bool done = false;
+        for (int w : {0, 4}) {
+            if (w && (!auto_warps || build)) break;
+            for (int h16 = (w == 0 ? 1 : 0); h16 < 2 && !done; ++h16) {
+                if (h16 && !auto_hash) continue;
+                Geometry g;
+                if (make_geometry(ix, k, L, false, build, &g, w, auto_hash ? h16 != 0 : true) != RG_OK) continue;
+                if (h16 && g.hash_kind != kHashGlobal16) continue;
+                if (fits(g)) {
+                    g1 = g;
+                    done = true;
+                }
             }
+            if (done) break;
+        }
+        if (!done && auto_hash) {
+            Geometry g;
+            if (make_geometry(ix, k, L, false, build, &g, 0, true) == RG_OK) g1 = g;
         }
     }
 
-    // scratch: overflow list (one slot per query) and global hash slabs (one per CTA)
+    // scratch: overflow list (one slot per query) and global hash slabs (one per CTA).  The fallback pass re-runs the few
+    // queries whose visited set outgrew the primary table with big 32-bit tables; its grid is kept small (64 CTAs) so that
+    // the scratch it needs (4 MB per CTA at L_pq = 500, 16 MB at the maximum table) stays modest on a device that already
+    // holds a 100M-row index.
     s = ensure((void **)&ix->d_overflow_list, &ix->overflow_cap, nq, sizeof(uint32_t));
     if (s != RG_OK) return s;
     const int grid1 = int(std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm));
-    const int grid2 = ix->sm_count * g2.ctas_per_sm;  // fallback pass: few, heavy queries
-    uint64_t need_hash = uint64_t(grid2) << g2.p.hash_log2;
-    if (g1.global_hash) need_hash = std::max(need_hash, uint64_t(grid1) << g1.p.hash_log2);
-    s = ensure((void **)&ix->d_ghash, &ix->ghash_words, need_hash, sizeof(uint32_t));
+    const int grid2 = int(std::min<uint64_t>(nq, 64));
+    const uint64_t need_bytes = std::max(uint64_t(grid2) * g2.slab_bytes, uint64_t(grid1) * g1.slab_bytes);
+    s = ensure((void **)&ix->d_ghash, &ix->ghash_words, (need_bytes + 3) / 4, sizeof(uint32_t));
     if (s != RG_OK) return s;
 
     for (Geometry *g : {&g1, &g2}) {
@@ -630,8 +796,8 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
         g->p.exp_cap = exp_cap;
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
-    const uint64_t slab_bytes = (uint64_t(grid1) << g1.p.hash_log2) * sizeof(uint32_t);
-    if (g1.global_hash && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
+    const uint64_t slab_bytes = uint64_t(grid1) * g1.slab_bytes;
+    if (g1.slab_bytes && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
         s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, st);
         if (s != RG_OK) return s;
@@ -686,15 +852,21 @@ uint32_t rg_search_last_overflow_count(rg_index *ix) {
     return v;
 }
 
-// Device-visible alias of a caller buffer when it is page-locked host memory (cudaHostAlloc / cudaHostRegister; under
-// unified addressing every such allocation is mapped), else nullptr.
-static void *mapped_alias(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+// Device-visible alias of a caller buffer when ALL of it is page-locked host memory (cudaHostAlloc / cudaHostRegister; under
+// unified addressing every such allocation is mapped), else nullptr.  First and last byte must belong to host
+// registrations whose device aliases are contiguous: a buffer that only shares its first page with a registered neighbour
+// (two small heap vectors on one page) must take the staged path.
+static void *mapped_alias(const void *p, uint64_t bytes) {
+    if (!bytes) return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
-    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+    if (static_cast<char *>(a1.devicePointer) - static_cast<char *>(a0.devicePointer) != ptrdiff_t(bytes - 1)) return nullptr;
+    return a0.devicePointer;
 }
 
 static rg_status report_status(const uint32_t status[2], uint32_t k, uint32_t L) {
@@ -730,11 +902,11 @@ rg_status rg_search_batch(rg_index *ix, const float *queries, uint64_t nq, uint3
     // transfers ride inside the search instead of in front of and behind it (8 MB in / 0.8 MB out per 10 000 queries
     // at D=200, k=10: 2 GB/s against >50 GB/s of PCIe, hidden behind the HBM-bound gathers of the other resident queries).
     if (ix->cfg_zero_copy) {
-        const float *zq = static_cast<const float *>(mapped_alias(queries));
-        uint32_t *zi = static_cast<uint32_t *>(mapped_alias(ids));
-        float *zd = static_cast<float *>(mapped_alias(dists));
-        uint32_t *zc = cmps ? static_cast<uint32_t *>(mapped_alias(cmps)) : nullptr;
-        uint32_t *zh = hops ? static_cast<uint32_t *>(mapped_alias(hops)) : nullptr;
+        const float *zq = static_cast<const float *>(mapped_alias(queries, nq * ix->dim * sizeof(float)));
+        uint32_t *zi = static_cast<uint32_t *>(mapped_alias(ids, nq * k * sizeof(uint32_t)));
+        float *zd = static_cast<float *>(mapped_alias(dists, nq * k * sizeof(float)));
+        uint32_t *zc = cmps ? static_cast<uint32_t *>(mapped_alias(cmps, nq * sizeof(uint32_t))) : nullptr;
+        uint32_t *zh = hops ? static_cast<uint32_t *>(mapped_alias(hops, nq * sizeof(uint32_t))) : nullptr;
         if (zq && zi && zd && (!cmps || zc) && (!hops || zh)) {
             s = rg::search_device(ix, zq, nq, k, L, zi, zd, zc, zh, d_status, st);
             if (s != RG_OK) return s;

@@ -17,6 +17,22 @@
 #include "index_bipartite.h"
 #include "roargraph_b200.h"
 
+template <typename T>
+struct PageAligned {  // zero-initialised, 4096-byte aligned array with the vector calls the driver uses
+    T *p = nullptr;
+    size_t n = 0;
+    explicit PageAligned(size_t count) : n(count) {
+        if (posix_memalign(reinterpret_cast<void **>(&p), 4096, std::max<size_t>(count, 1) * sizeof(T)) != 0) throw std::bad_alloc();
+        memset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    ~PageAligned() { free(p); }
+    PageAligned(const PageAligned &) = delete;
+    PageAligned &operator=(const PageAligned &) = delete;
+    T *data() { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+};
+
 // tests/test_search_roargraph.cpp:23-36
 static float ComputeRecall(uint32_t q_num, uint32_t k, uint32_t gt_dim, const uint32_t *res, const uint32_t *gt) {
     uint32_t hit = 0;
@@ -64,7 +80,13 @@ int main(int argc, char **argv) {
     efanna2e::load_meta<float>(query_file.c_str(), q_pts, q_dim);
     float *query_data = nullptr;
     efanna2e::load_data<float>(query_file.c_str(), q_pts, q_dim, query_data);
-    float *aligned_query_data = efanna2e::data_align(query_data, q_pts, q_dim);
+    // load_data already returns rows padded to 8 floats, so the reference's follow-up data_align(query_data, q_pts, q_dim)
+    // (tests/test_search_roargraph.cpp:166) would re-read the padded buffer with the unpadded stride and scramble every row
+    // after the first when dim % 8 != 0 (the reference has that latent bug for base and queries alike; all its datasets have
+    // dim % 8 == 0).  The loaded buffer IS the aligned one; only the row length changes.
+    float *aligned_query_data = query_data;
+    q_dim = (uint32_t)efanna2e::padded_dim(q_dim);
+    std::cout << "new_dim: " << q_dim << std::endl;
 
     uint32_t gt_pts, gt_dim;
     uint32_t *gt_ids = nullptr;
@@ -101,8 +123,9 @@ int main(int argc, char **argv) {
     index.InitVisitedListPool(num_threads);  // uploads base + graph to the GPU
 
     std::cout << "k: " << k << std::endl;
-    std::vector<uint32_t> res((size_t)q_pts * k, 0), cmps(q_pts, 0), hops(q_pts, 0);
-    std::vector<float> res_dists((size_t)q_pts * k, 0.f);
+    // result arrays on their own pages: two small heap vectors sharing a page cannot both be page-locked
+    PageAligned<uint32_t> res((size_t)q_pts * k), cmps(q_pts), hops(q_pts);
+    PageAligned<float> res_dists((size_t)q_pts * k);
     // page-lock the query and result arrays: rg_search_batch then reads/writes them in place (no staging copies)
     const std::pair<void *, size_t> pinned[] = {{aligned_query_data, (size_t)q_pts * q_dim * sizeof(float)},
                                                 {res.data(), res.size() * sizeof(uint32_t)},

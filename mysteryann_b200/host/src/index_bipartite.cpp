@@ -93,11 +93,22 @@ void IndexBipartite::LoadProjectionGraph(const char *filename) {
     in.read(reinterpret_cast<char *>(&projection_ep_), sizeof(uint32_t));
     in.read(reinterpret_cast<char *>(&npts), sizeof(uint32_t));
     std::cout << "Projection graph, ep: " << projection_ep_ << std::endl;
+    // header and degree words are checked against the bytes that are really there: a truncated or foreign file must not
+    // turn into a huge resize here or into out-of-range row gathers on the GPU
+    in.seekg(0, std::ios::end);
+    const uint64_t file_bytes = static_cast<uint64_t>(in.tellg());
+    in.seekg(2 * sizeof(uint32_t), std::ios::beg);
+    if (!in || file_bytes < 2 * sizeof(uint32_t) || uint64_t(npts) * sizeof(uint32_t) > file_bytes - 2 * sizeof(uint32_t))
+        throw std::runtime_error("projection graph file truncated");
+    uint64_t left = file_bytes - 2 * sizeof(uint32_t);
     projection_graph_.assign(npts, {});
     double total = 0;
     for (uint32_t i = 0; i < npts; ++i) {
         uint32_t deg = 0;
         in.read(reinterpret_cast<char *>(&deg), sizeof(uint32_t));
+        if (!in || left < sizeof(uint32_t) || uint64_t(deg) * sizeof(uint32_t) > left - sizeof(uint32_t))
+            throw std::runtime_error("projection graph file truncated");
+        left -= sizeof(uint32_t) + uint64_t(deg) * sizeof(uint32_t);
         projection_graph_[i].resize(deg);
         in.read(reinterpret_cast<char *>(projection_graph_[i].data()), std::streamsize(deg) * sizeof(uint32_t));
         total += deg;

@@ -2,21 +2,21 @@
 
 Same decomposition as the reference's tool, which walks the base in parts of 20M points sequentially and merges the
 per-part top-k (thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:32, 396-448); here the parts are the ranks of
-one 8xB200 box (one process per GPU, torch.distributed):
+one 8xB200 box (one process per GPU).  Rank g holds base rows [lo_g, hi_g) and all queries and ends up with the merged
+lists of query slice g.
 
-  1. every rank holds base rows [lo_g, hi_g) and runs K2/K3 (rg_knn_exact_device) for ALL queries against its shard,
-     ids already global (id_base = lo_g)                                          -> part lists [nq, K]
-  2. one all-to-all over NVLink (NCCL): rank g receives, from every rank, the part lists of query slice g
-                                                                                  -> [G, nq_g, K]
-  3. K4 (rg_knn_merge_device) merges the G sorted lists of each query             -> [nq_g, K]
-  4. optional all-gather of the merged slices (the learn->base file is written by one rank).
+Product path `knn_sharded`: one call of the C ABI entry rg_knn_exact_sharded (csrc/rg_knn_sharded.cu) per rank - K2/K3
+per shard and query chunk, grouped ncclSend/ncclRecv of the per-shard lists over NVLink, K4 merge, all issued by the
+library on its own NCCL communicator.  torch.distributed is only the side channel that hands the ncclUniqueId to the
+ranks (`nccl_comm_for`) and, optionally, all-gathers the merged slices (the learn->base file is written by one rank).
 
 Exchange volume per rank: (G-1)/G * nq * K * 8 bytes in and out (C4, nq = 10M, K = 100, G = 8: 7 GB, ~10 ms at the
-measured 770 GB/s per direction) against ~5 PFLOP of GEMM per rank, so the exchange is not overlapped.
+measured 770 GB/s per direction) against ~5 PFLOP of GEMM per rank.
 
-The functions take the process group explicitly and work on whatever device the tensors live on, so the exchange
-logic is covered by world_size-2 gloo tests on CPU (tests/test_sharded_knn_cpu.py, with the oracle standing in for
-the CUDA kernels); the product path (`knn_sharded`) only runs on CUDA tensors.
+`knn_sharded_with` is the same algorithm with the two compute steps injected and torch.distributed's all-to-all as the
+exchange: it runs on whatever device the tensors live on, so the shard bounds, the exchange layout and the gather are
+covered by world_size-2/4 gloo tests on CPU (tests/test_sharded_knn_cpu.py, with the oracle standing in for the CUDA
+kernels); `knn_sharded_torch` is that variant with the CUDA kernels (round 1's path, kept as a yardstick).
 """
 from __future__ import annotations
 
@@ -127,10 +127,60 @@ def knn_sharded_with(local_knn: Callable, merge: Callable, queries: torch.Tensor
     return gather_rows(mid, qb, group), gather_rows(md, qb, group), qb
 
 
+_COMMS = {}  # process-group id -> (ncclComm_t handle, rank in group, group size)
+
+
+def nccl_comm_for(group=None, device: Optional[int] = None):
+    """The library's own NCCL communicator for `group` (created once): the 128-byte ncclUniqueId is made by the group's
+    first rank through the C ABI (rg_nccl_get_unique_id) and handed to the others with a torch.distributed broadcast -
+    torch only plays the side channel; the exchange itself is issued by rg_knn_exact_sharded.  Collective over the group."""
+    from . import capi
+
+    key = id(group) if group is not None else 0
+    if key in _COMMS:
+        return _COMMS[key]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    device = torch.cuda.current_device() if device is None else device
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    if dist.get_rank() == src:
+        uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).clone()
+    else:
+        uid = torch.zeros(128, dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        uid = uid.cuda(device)
+    dist.broadcast(uid, src=src, group=group)
+    comm = capi.nccl_comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()), device)
+    _COMMS[key] = (comm, rank, world)
+    return _COMMS[key]
+
+
 def knn_sharded(d_base_shard: torch.Tensor, id_base: int, d_queries: torch.Tensor, K: int, metric: int = 1, group=None,
                 gather: bool = True, stream: Optional[int] = None):
-    """Product path (CUDA tensors, NCCL group): exact top-K of every query over the union of all ranks' base shards.
+    """Product path (CUDA tensors): exact top-K of every query over the union of all ranks' base shards through the C ABI
+    entry rg_knn_exact_sharded (K2/K3 per shard, grouped ncclSend/ncclRecv exchange, K4 merge - all inside the library).
     Returns (ids int32 [nq or nq_g, K], dists float32, query bounds).  Raises if the CUDA library or a device is missing."""
+    from . import capi
+
+    if not (d_base_shard.is_cuda and d_queries.is_cuda):
+        raise capi.RoarGraphError(capi.RG_ERR_NO_DEVICE, "knn_sharded needs CUDA tensors (there is no CPU fallback)")
+    comm, rank, world = nccl_comm_for(group, d_base_shard.device.index or 0)
+    nq = d_queries.shape[0]
+    qb = shard_bounds(nq, world)
+    assert (qb[rank], qb[rank + 1]) == capi.knn_sharded_slice(nq, rank, world)
+    mine = qb[rank + 1] - qb[rank]
+    ids = torch.empty((mine, K), dtype=torch.int32, device=d_queries.device)
+    d = torch.empty((mine, K), dtype=torch.float32, device=d_queries.device)
+    capi.knn_exact_sharded(d_base_shard, id_base, d_queries, K, ids, d, comm, rank, world, metric=metric, stream=stream)
+    if not gather:
+        return ids, d, qb
+    return gather_rows(ids, qb, group), gather_rows(d, qb, group), qb
+
+
+def knn_sharded_torch(d_base_shard: torch.Tensor, id_base: int, d_queries: torch.Tensor, K: int, metric: int = 1, group=None,
+                      gather: bool = True, stream: Optional[int] = None):
+    """The same decomposition with torch.distributed's all-to-all as the exchange (round 1's path; kept as the yardstick
+    tools/bench_knn_sharded.py compares the C-ABI path against)."""
     from . import capi
 
     if not (d_base_shard.is_cuda and d_queries.is_cuda):

@@ -197,6 +197,62 @@ def test_search_driver_l2_and_cosine(bins, oracle, tmp_path):
         assert abs(r[2] - want["cmps"].mean()) < 5e-3 * want["cmps"].mean() and abs(r[5] - want["hops"].mean()) < 0.5, r
 
 
+def test_search_driver_unpadded_dim(bins, oracle, tmp_path):
+    """dim % 8 != 0 (D = 100): the loader pads rows to 104 floats once, for base and queries alike (the reference re-aligns
+    the already padded query buffer with the unpadded stride, tests/test_search_roargraph.cpp:166 - a latent bug every one of
+    its datasets avoids by having dim % 8 == 0).  The CSV must equal the oracle's numbers on zero-padded rows."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(23)
+    n, dim, nq = 2500, 100, 120
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    test = (rng.standard_normal((nq, dim)) + 0.2).astype(np.float32)
+    deg = rng.integers(6, 20, n)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=off[1:])
+    adj = rng.integers(0, n, int(off[-1])).astype(np.uint32)
+    io.write_fbin(tmp_path / "base.fbin", base)
+    io.write_fbin(tmp_path / "test.fbin", test)
+    io.write_index(tmp_path / "rnd.index", 3, off, adj)
+    gt, gd, _ = oracle.exact_knn(pad8(base), pad8(test), 50, metric=1)
+    io.write_ibin(tmp_path / "gt.bin", gt, gd)
+    run([os.path.join(bins, "test_search_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path",
+         str(tmp_path / "base.fbin"), "--query_path", str(tmp_path / "test.fbin"), "--gt_path", str(tmp_path / "gt.bin"),
+         "--projection_index_save_path", str(tmp_path / "rnd.index"), "--k", "10", "--evaluation_save_path",
+         str(tmp_path / "out.csv"), "--L_pq", "10", "40"])
+    rows = [[float(v) for v in line.strip().split(",")] for line in open(tmp_path / "out.csv") if line.strip()]
+    assert [int(r[0]) for r in rows] == [10, 40]
+    for r in rows:
+        want = oracle.search(pad8(base), off, adj, 3, pad8(test), 10, int(r[0]), metric=1)
+        assert abs(r[4] - oracle.recall(want["ids"], gt, 10)) < 1e-5, r
+        assert abs(r[2] - want["cmps"].mean()) < 1e-2 and abs(r[5] - want["hops"].mean()) < 1e-2, r
+
+
+def test_search_driver_rejects_foreign_index(bins, tmp_path):
+    """An index file whose neighbour ids or degree words do not fit the base must be refused before anything reaches the GPU."""
+    from mysteryann_b200 import io
+
+    rng = np.random.default_rng(29)
+    base = rng.standard_normal((200, 16)).astype(np.float32)
+    io.write_fbin(tmp_path / "base.fbin", base)
+    io.write_fbin(tmp_path / "test.fbin", base[:10])
+    io.write_ibin(tmp_path / "gt.bin", np.zeros((10, 10), np.uint32), np.zeros((10, 10), np.float32))
+    off = np.arange(0, 201 * 4, 4, dtype=np.uint64)
+    adj = rng.integers(0, 200, 800).astype(np.uint32)
+    adj[123] = 5000                                        # out of range
+    io.write_index(tmp_path / "bad_id.index", 0, off, adj)
+    raw = np.fromfile(tmp_path / "bad_id.index", dtype=np.uint32).copy()
+    raw[2] = 0x7FFFFFF0                                    # absurd degree word of node 0
+    raw.tofile(tmp_path / "bad_deg.index")
+    for name in ("bad_id.index", "bad_deg.index"):
+        p = subprocess.run([os.path.join(bins, "test_search_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path",
+                            str(tmp_path / "base.fbin"), "--query_path", str(tmp_path / "test.fbin"), "--gt_path", str(tmp_path / "gt.bin"),
+                            "--projection_index_save_path", str(tmp_path / name), "--k", "10", "--L_pq", "10"],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode != 0, name
+        assert "out of range" in (p.stdout + p.stderr) or "truncated" in (p.stdout + p.stderr), p.stdout + p.stderr
+
+
 def test_per_query_api_from_openmp_threads(tmp_path):
     """Existing callers of the reference call IndexBipartite::SearchRoarGraph once per query from OpenMP threads
     (tests/test_search_roargraph.cpp:203-209).  The drop-in class must give the reference's answers that way too

@@ -85,3 +85,128 @@ def test_knn_device_api_and_merge(capi, oracle):
     capi.knn_merge_device(part_ids, part_d, out_ids, out_d, metric=1)
     torch.cuda.synchronize()
     check_knn(out_ids.cpu().numpy().view(np.uint32), out_d.cpu().numpy(), want_ids, want_d, "merge")
+
+
+@pytest.mark.parametrize("metric", (1, 0))
+def test_knn_query_batches(capi, oracle, metric, monkeypatch):
+    """More queries than one K2 batch: the batch loop (per-batch FP16 conversion, candidate lists, flag offsets) against the
+    oracle - once with the batch size forced down to 4096 (three batches, the last one ragged), once with the default
+    131072 crossed by 140000 queries."""
+    from mysteryann_b200 import synth
+
+    base, train, _ = synth.make_numpy(20000, 10000, 1, 64, seed=77)
+    want_ids, want_d, _ = oracle.exact_knn(base, train, 10, metric=metric)
+    monkeypatch.setenv("RG_KNN_QBATCH", "4096")
+    ids, d = capi.knn_exact(base, train, 10, metric=metric)
+    check_knn(ids, d, want_ids, want_d, f"q_batch=4096 metric={metric}")
+    monkeypatch.delenv("RG_KNN_QBATCH")
+    base, train, _ = synth.make_numpy(3000, 140000, 1, 64, seed=78)
+    want_ids, want_d, _ = oracle.exact_knn(base, train, 10, metric=metric)
+    ids, d = capi.knn_exact(base, train, 10, metric=metric)
+    check_knn(ids, d, want_ids, want_d, f"nq=140000 metric={metric}")
+
+
+@pytest.mark.parametrize("metric,optimistic", ((1, 1), (0, 1), (1, 0)))
+def test_knn_million_row_base_sample(capi, oracle, metric, optimistic, monkeypatch):
+    """1.2M base rows x 20000 queries on the GPU (block schedule far past 64K rows, sparse epilogue at depth, the
+    optimistic threshold ranks r < k' in play), 256 sampled queries against the oracle; both threshold schedules."""
+    import torch
+
+    monkeypatch.setenv("RG_KNN_OPTIMISTIC", str(optimistic))
+    rng = np.random.default_rng(123 + metric)
+    n, nq, dim, K = 1_200_000, 20000, 64, 100
+    base = rng.standard_normal((n, dim), dtype=np.float32)
+    q = rng.standard_normal((nq, dim), dtype=np.float32) + 0.25
+    db, dq = torch.from_numpy(base).cuda(), torch.from_numpy(q).cuda()
+    ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+    d = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+    capi.knn_exact_device(db, dq, K, ids, d, metric=metric)
+    st = capi.knn_last_stats()
+    assert st["exact_scans"] <= 2 and st["second_pass"] <= nq // 100, st
+    sample = rng.choice(nq, 256, replace=False)
+    want_ids, want_d, _ = oracle.exact_knn(base, q[sample], K, metric=metric)
+    check_knn(ids.cpu().numpy().view(np.uint32)[sample], d.cpu().numpy()[sample], want_ids, want_d,
+              f"1.2M rows metric={metric} optimistic={optimistic}")
+    capi.knn_release_scratch()
+
+
+def test_knn_best_rows_first_takes_second_pass(capi, oracle):
+    """Rows stored best-first: the optimistic schedule takes its threshold from the first block, nothing later beats it,
+    the lists end with fewer than K survivors, the certificate fails - and the conservative second pass must return the
+    exact answer without resorting to the FP32 scan."""
+    rng = np.random.default_rng(2)
+    dim, n, K = 32, 60_000, 50
+    direction = rng.standard_normal(dim).astype(np.float32)
+    # <q,b> decreases with the row index, ~1.5 % between ranks K and k' (well above the FP16 rounding bound of the certificate)
+    scale = (4.0 * np.exp(-np.arange(n, dtype=np.float64) / 2000.0)).astype(np.float32)[:, None]
+    base = (scale * direction[None, :] + 0.0002 * rng.standard_normal((n, dim))).astype(np.float32)
+    q = (direction[None, :] + 0.01 * rng.standard_normal((64, dim))).astype(np.float32)
+    want_ids, want_d, _ = oracle.exact_knn(base, q, K, metric=1)
+    ids, d = capi.knn_exact(base, q, K, metric=1)
+    check_knn(ids, d, want_ids, want_d, "best-first")
+    st = capi.knn_last_stats()
+    assert st["second_pass"] > 0 and st["exact_scans"] == 0, st
+
+
+def test_knn_sharded_capi_world1(capi, oracle):
+    """rg_knn_exact_sharded with world = 1 (no communicator): the slice is the whole query set."""
+    import torch
+    from mysteryann_b200 import synth
+
+    base, q, _ = synth.make_numpy(6000, 300, 1, 200, seed=9)
+    K = 20
+    want_ids, want_d, _ = oracle.exact_knn(base, q, K, metric=1)
+    db, dq = torch.from_numpy(base).cuda(), torch.from_numpy(q).cuda()
+    assert capi.knn_sharded_slice(300, 0, 1) == (0, 300)
+    assert capi.knn_sharded_slice(10, 1, 3) == (4, 7)
+    ids = torch.empty((300, K), dtype=torch.int32, device="cuda")
+    d = torch.empty((300, K), dtype=torch.float32, device="cuda")
+    capi.knn_exact_sharded(db, 0, dq, K, ids, d, None, 0, 1, metric=1)
+    check_knn(ids.cpu().numpy().view(np.uint32), d.cpu().numpy(), want_ids, want_d, "sharded world=1")
+    with pytest.raises(capi.RoarGraphError):   # world > 1 needs a communicator
+        capi.knn_exact_sharded(db, 0, dq, K, ids, d, None, 0, 2, metric=1)
+
+
+def test_knn_sharded_capi_two_gpus(capi, oracle):
+    """Two base shards on two GPUs, one host thread per GPU (the layout of compute_groundtruth --devices 2): communicators
+    from rg_nccl_comm_init_all, grouped ncclSend/ncclRecv exchange and K4 merge inside rg_knn_exact_sharded.  Skipped on a
+    one-GPU box."""
+    import ctypes as C
+    import threading
+
+    import torch
+    from mysteryann_b200 import synth
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert capi.lib().rg_nccl_version() > 0
+    n, nq, dim, K = 30000, 1001, 200, 30
+    base, q, _ = synth.make_numpy(n, nq, 1, dim, seed=12)
+    want_ids, want_d, _ = oracle.exact_knn(base, q, K, metric=1)
+    comms = (C.c_void_p * 2)()
+    assert capi.lib().rg_nccl_comm_init_all(comms, 2, None) == 0, capi.lib().rg_last_error_string()
+    bounds = [0, 17000, n]
+    out, err = [None, None], [None, None]
+
+    def work(r):
+        try:
+            dev = torch.device("cuda", r)
+            with torch.cuda.device(dev):
+                shard = torch.from_numpy(base[bounds[r]:bounds[r + 1]]).to(dev)
+                dq = torch.from_numpy(q).to(dev)
+                lo, hi = capi.knn_sharded_slice(nq, r, 2)
+                ids = torch.empty((hi - lo, K), dtype=torch.int32, device=dev)
+                d = torch.empty((hi - lo, K), dtype=torch.float32, device=dev)
+                capi.knn_exact_sharded(shard, bounds[r], dq, K, ids, d, C.c_void_p(comms[r]), r, 2, metric=1)
+                out[r] = (lo, hi, ids.cpu().numpy().view(np.uint32), d.cpu().numpy())
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert err == [None, None], err
+    for r in range(2):
+        lo, hi, ids, d = out[r]
+        check_knn(ids, d, want_ids[lo:hi], want_d[lo:hi], f"sharded rank {r}")
+        capi.nccl_comm_destroy(C.c_void_p(comms[r]))

@@ -41,16 +41,25 @@ def capi():
 
 # (gather, warps per query, visited-hash space, L2 hints, adjacency prefetch): cp.async / TMA bulk gathers, 1..8 warps per
 # query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch
-CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 2, 0, 0), (2, 1, 1, 0, 0), (2, 2, 2, 3, 3), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2),
-           (2, 2, 2, 2, 1), (2, 2, 2, 0, 0))
+# hash space: 1 shared memory, 2 global 32-bit keys, 3 global 16-bit quotient entries, 0 auto (= 3 where the id range allows);
+# a sixth field, when present, is the number of row staging buffers per warp (2 = gather ring)
+CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3, 2), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2, 2),
+           (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 3, 3, 1, 2))
 
 
-@pytest.mark.parametrize("gather,warps,space,l2,pf", CONFIGS)
+def configure(ix, cfg, **kw):
+    gather, warps, space, l2, pf = cfg[:5]
+    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf,
+                 stage_bufs=cfg[5] if len(cfg) > 5 else 0, **kw)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("name", CASES)
-def test_golden(capi, name, gather, warps, space, l2, pf):
+def test_golden(capi, name, cfg):
     c = load_case(name)
     ix = capi.Index(c["base"], c["offsets"], c["adj"], c["ep"], metric=c["metric"])
-    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf)
+    configure(ix, cfg)
+    gather, warps, space, l2, pf = cfg[:5]
     for L in c["Ls"]:
         L = int(L)
         got = ix.search(c["test"], 10, L)
@@ -82,8 +91,9 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     if off[ep + 1] == off[ep]:
         ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    for gather, warps, space, l2, pf in CONFIGS[:5]:
-        ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf)
+    for cfg in CONFIGS[:5] + CONFIGS[8:]:
+        configure(ix, cfg)
+        gather, warps, space = cfg[:3]
         for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
             want = oracle.search(base, off, adj, ep, q, k, L, metric=metric)
             got = ix.search(q, k, L)
@@ -102,11 +112,29 @@ def test_visited_overflow_takes_exact_fallback(capi, oracle):
     ix = capi.Index(base, off, adj, 3, metric=1)
     want = oracle.search(base, off, adj, 3, q, 10, 50, metric=1)
     assert want["cmps"].max() > 256
-    for space in (1, 2):
+    for space in (1, 2, 3):
         ix.configure(hash_log2=8, hash_space=space)
         report(f"overflow space={space}", ix.search(q, 10, 50), want)
+        assert ix.last_overflow > 100
     ix.configure(hash_log2=16, hash_space=1)   # > 15: too big for shared memory, global tables are used anyway
     report("global-primary", ix.search(q, 10, 50), want)
+    ix.close()
+
+
+def test_hash16_displacement_exhausted(capi, oracle):
+    """16-bit quotient visited set on a 2^20-id range with a 1024-slot table: 10 remainder bits leave 6 displacement bits,
+    so long probe runs exhaust the field before the load limit and those queries take the exact big-table pass."""
+    rng = np.random.default_rng(11)
+    n, dim = 1 << 20, 8
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((300, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 4, 12)
+    ix = capi.Index(base, off, adj, 5, metric=0)
+    want = oracle.search(base, off, adj, 5, q, 10, 80, metric=0)
+    for hl, lo, hi in ((10, 1, 300), (12, 0, 299)):
+        ix.configure(hash_log2=hl, hash_space=3)
+        report(f"hash16 hl={hl}", ix.search(q, 10, 80), want)
+        assert lo <= ix.last_overflow <= hi
     ix.close()
 
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--check", type=int, default=4096, help="queries verified against the unsharded answer (0 = none)")
     ap.add_argument("--base-shards", type=int, default=0, help="2-D layout: base shards x query groups (sharded_knn.Grid); "
                                                              "0 = one base shard per rank, the scheme of config C4")
+    ap.add_argument("--exchange", default="capi", choices=["capi", "torch"],
+                    help="capi = rg_knn_exact_sharded (grouped ncclSend/ncclRecv inside the library), torch = all_to_all_single")
     ap.add_argument("--warm", type=int, default=65536, help="queries of the untimed warm-up call (NCCL channels, scratch allocation)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -39,12 +41,13 @@ def main():
     dist.barrier()
     base, train, _ = synth.make_torch(a.n, a.nq, 1, a.dim, device=dev)   # same seed on every rank: identical data
     st = torch.cuda.current_stream().cuda_stream
+    knn = sharded_knn.knn_sharded if a.exchange == "capi" else sharded_knn.knn_sharded_torch
     if a.base_shards in (0, world):
         b = sharded_knn.shard_bounds(a.n, world)
         shard = base[b[rank]:b[rank + 1]]
 
         def run(q=train):
-            return sharded_knn.knn_sharded(shard, b[rank], q, a.K, metric=capi.METRIC_IP, gather=False, stream=st)
+            return knn(shard, b[rank], q, a.K, metric=capi.METRIC_IP, gather=False, stream=st)
     else:
         # base shards x query groups: this rank answers its group's queries against its base shard; the exchange and the
         # merge run inside the group.  `qb` below are the bounds of the merged slices in rank order.
@@ -54,7 +57,7 @@ def main():
 
         def run(q=train):
             q0, q1 = grid.query_bounds(q.shape[0])
-            ids, d, _ = sharded_knn.knn_sharded(shard, lo, q[q0:q1].contiguous(), a.K, metric=capi.METRIC_IP, group=grid.group,
+            ids, d, _ = knn(shard, lo, q[q0:q1].contiguous(), a.K, metric=capi.METRIC_IP, group=grid.group,
                                                 gather=False, stream=st)
             return ids, d, grid.result_bounds(q.shape[0])
 
@@ -86,7 +89,8 @@ def main():
                               tflops_per_gpu=round(flops / (ms * 1e-3) / 1e12 / world, 1),
                               c4_extrapolated_s=round(ms * 1e-3 * (10_000_000 / a.nq) * (10_000_000 / a.n), 1),
                               sharded_equals_unsharded=ok, base_shards=a.base_shards or world,
-                              exchange="NCCL all_to_all_single + K4 merge")), flush=True)
+                              exchange="rg_knn_exact_sharded: grouped ncclSend/ncclRecv + K4 merge" if a.exchange == "capi"
+                              else "torch all_to_all_single + K4 merge", knn_stats=capi.knn_last_stats())), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
