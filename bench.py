@@ -57,7 +57,6 @@ def parse_args():
     ap.add_argument("--stage-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per query (0 = library default)")
     ap.add_argument("--hash-space", type=int, default=0)
-    ap.add_argument("--stage-bufs", type=int, default=0, help="row staging buffers per warp (0 = library default)")
     ap.add_argument("--ctas", type=int, default=0, help="resident K1 CTAs per SM (0 = library default)")
     ap.add_argument("--hash-log2", type=int, default=0, help="visited-hash slots per query, log2 (0 = library default)")
     ap.add_argument("--l2-hint", type=int, default=None, help="K1 L2 policy bit mask (None = library default)")
@@ -381,7 +380,7 @@ def run_ours(args):
     ix = d["index"]
     ix.configure(gather=args.gather, warps_per_query=args.warps, ctas_per_sm=args.ctas, stage_rows=args.stage_rows,
                  hash_log2=args.hash_log2, hash_space=args.hash_space,
-                 l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch, stage_bufs=args.stage_bufs)
+                 l2_hint=args.l2_hint, adj_prefetch=args.adj_prefetch)
     ix.set_option("zero_copy", args.zero_copy)
     q = d["queries"]
     ids = torch.empty((nq, k), dtype=torch.int32, device=device)

@@ -90,7 +90,6 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
                                      int hash_log2);
 /* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory with 32-bit keys (L2-resident
  * slab per CTA), 3 in global memory with 16-bit quotient entries where the id range allows (what auto picks);
- * "stage_bufs" = 0 auto, 1 or 2 row staging buffers per warp (2: the next batch of rows is in flight while one is scored);
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
  * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its
@@ -158,6 +157,12 @@ RG_API rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shar
                                       const float *d_queries, uint64_t nq, uint32_t dim, int metric, uint32_t K,
                                       uint32_t *d_ids, float *d_dists, void *nccl_comm, int rank, int world,
                                       int device, void *cuda_stream);
+/* Host-buffer variant (H2D of the shard and the queries, the call above on a private stream, D2H of the slice): ids / dists
+ * are host arrays of (hi - lo) x K entries.  Used by the compute_groundtruth driver, one host thread per GPU. */
+RG_API rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, uint64_t id_base,
+                                           const float *queries, uint64_t nq, uint32_t dim, int metric, uint32_t K,
+                                           uint32_t *ids, float *dists, void *nccl_comm, int rank, int world,
+                                           int device);
 /* Query rows [*lo, *hi) whose merged lists rank `rank` of `world` receives (contiguous, ascending with the rank; the first
  * nq % world slices hold one extra row). */
 RG_API void rg_knn_sharded_slice(uint64_t nq, int rank, int world, uint64_t *lo, uint64_t *hi);
@@ -185,6 +190,12 @@ RG_API rg_status rg_build_roargraph_device(const float *d_base, uint64_t n, uint
                                            const uint32_t *d_knn_ids, uint64_t n_train, uint32_t knn_k, uint32_t M_sq,
                                            uint32_t M_pjbp, uint32_t L_pjpq, rg_graph **out, int device,
                                            void *cuda_stream);
+/* Diagnostic: only the pivot projection prune of every training query (PruneBiSearchBaseGetBase, :1059-1097, 1612-1694),
+ * the deterministic first phase of the build: d_lists [n_train][M_pjbp + 1], word 0 = list length. */
+RG_API rg_status rg_build_projection_lists_device(const float *d_base, uint64_t n, uint32_t dim, int metric,
+                                                  const uint32_t *d_knn_ids, uint64_t n_train, uint32_t knn_k,
+                                                  uint32_t M_sq, uint32_t M_pjbp, uint32_t *d_lists, int device,
+                                                  void *cuda_stream);
 /* Host-buffer variant (what the drop-in IndexBipartite::BuildRoarGraph calls when Parameters holds "gpu_build" != 0):
  * base and knn_ids are host memory; they are uploaded for the duration of the build. */
 RG_API rg_status rg_build_roargraph(const float *base, uint64_t n, uint32_t dim, int metric, const uint32_t *knn_ids,

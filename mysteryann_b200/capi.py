@@ -23,7 +23,7 @@ SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_i
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
            "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
-           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded",
+           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
            "rg_knn_sharded_slice", "rg_nccl_get_unique_id", "rg_nccl_comm_init_rank", "rg_nccl_comm_init_all",
            "rg_nccl_comm_destroy", "rg_nccl_version"]
 
@@ -86,6 +86,8 @@ def lib():
     L.rg_knn_release_scratch.argtypes = [i32]
     L.rg_knn_exact_sharded.restype = i32
     L.rg_knn_exact_sharded.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32, vp]
+    L.rg_knn_exact_sharded_host.restype = i32
+    L.rg_knn_exact_sharded_host.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32]
     L.rg_knn_sharded_slice.restype = None
     L.rg_knn_sharded_slice.argtypes = [u64, i32, i32, vp, vp]
     L.rg_nccl_get_unique_id.restype = i32
@@ -99,6 +101,8 @@ def lib():
     L.rg_nccl_version.restype = i32
     L.rg_build_roargraph_device.restype = i32
     L.rg_build_roargraph_device.argtypes = [vp, u64, u32, i32, vp, u64, u32, u32, u32, u32, C.POINTER(vp), i32, vp]
+    L.rg_build_projection_lists_device.restype = i32
+    L.rg_build_projection_lists_device.argtypes = [vp, u64, u32, i32, vp, u64, u32, u32, u32, vp, i32, vp]
     L.rg_graph_info.restype = i32
     L.rg_graph_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rg_graph_download.restype = i32
@@ -167,17 +171,16 @@ class Index:
     __del__ = close
 
     def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0,
-                  l2_hint=None, adj_prefetch=None, stage_bufs=0):
+                  l2_hint=None, adj_prefetch=None):
         _check(lib().rg_search_configure(self._h, gather, warps_per_query, ctas_per_sm, stage_rows, hash_log2))
         _check(lib().rg_search_set_option(self._h, b"hash_space", hash_space))
-        _check(lib().rg_search_set_option(self._h, b"stage_bufs", stage_bufs))
         if l2_hint is not None:
             _check(lib().rg_search_set_option(self._h, b"l2_hint", l2_hint))
         if adj_prefetch is not None:
             _check(lib().rg_search_set_option(self._h, b"adj_prefetch", adj_prefetch))
 
     def set_option(self, name: str, value: int):
-        """Named option of rg_search_set_option ("hash_space", "stage_bufs", "l2_hint", "adj_prefetch", "zero_copy")."""
+        """Named option of rg_search_set_option ("hash_space", "l2_hint", "adj_prefetch", "zero_copy")."""
         _check(lib().rg_search_set_option(self._h, name.encode(), int(value)))
 
     @property
@@ -245,6 +248,18 @@ class Graph:
             self._h = None
 
     __del__ = close
+
+
+def projection_lists_device(d_base, d_knn_ids, M_sq=100, M_pjbp=35, metric=METRIC_IP):
+    """P1 of the GPU build only: per-training-query pruned lists, torch int32 [n_train, M_pjbp + 1] (column 0 = length)."""
+    import torch
+
+    n, dim = d_base.shape
+    n_train, K = d_knn_ids.shape
+    out = torch.zeros((n_train, M_pjbp + 1), dtype=torch.int32, device=d_base.device)
+    _check(lib().rg_build_projection_lists_device(d_base.data_ptr(), n, dim, metric, d_knn_ids.data_ptr(), n_train, K, M_sq, M_pjbp,
+                                                  out.data_ptr(), d_base.device.index or 0, None))
+    return out
 
 
 def knn_exact(base, queries, K, metric=METRIC_IP, id_base=0, device=0):

@@ -455,8 +455,12 @@ static double now_s() {
 
 static uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// d_p1_lists != nullptr: stop after the pivot projection prune (P1) and hand out its per-training-query lists
+// ([n_train][M + 1], word 0 = length) - the deterministic part of the build, compared list by list with the host's
+// PruneBiSearchBaseGetBase restatement by tests/test_build_gpu.py
 rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric, const uint32_t *d_knn, uint64_t n_train,
-                       uint32_t knn_k, uint32_t M_sq, uint32_t M, uint32_t L_pjpq, rg_graph *g, cudaStream_t st) {
+                       uint32_t knn_k, uint32_t M_sq, uint32_t M, uint32_t L_pjpq, rg_graph *g, cudaStream_t st,
+                       uint32_t *d_p1_lists = nullptr) {
     const bool ip = metric != RG_METRIC_L2;
     int dev = 0, sms = 0, smem_max = 0;
     RG_CUDA_OK(cudaGetDevice(&dev));
@@ -554,6 +558,11 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     const unsigned tb = unsigned((n_train + 255) / 256);
     pivot_owner_kernel<<<tb, 256, 0, st>>>(d_knn, n_train, knn_k, n, owner);
     RG_CUDA_OK(run_prune(kProjection, uint32_t(n_train)));
+    if (d_p1_lists) {
+        RG_CUDA_OK(cudaMemcpyAsync(d_p1_lists, T, n_train * uint64_t(M + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        return RG_OK;
+    }
     copy_owner_lists_kernel<<<wide, 256, 0, st>>>(d_knn, n_train, knn_k, n, owner, T, M, P, stride);
     RG_CUDA_OK(cudaStreamSynchronize(st));
     g->seconds[1] = now_s() - t0;
@@ -830,4 +839,23 @@ rg_status rg_index_create_from_graph(rg_index **out, const float *d_base, uint64
     return RG_OK;
 }
 
+
+// Diagnostic: only the pivot projection prune (P1, PruneBiSearchBaseGetBase src/index_bipartite.cpp:1059-1097, 1612-1694) of
+// every training query; d_lists [n_train][M_pjbp + 1] (word 0 = list length).  Deterministic given the kNN ids.
+rg_status rg_build_projection_lists_device(const float *d_base, uint64_t n, uint32_t dim, int metric, const uint32_t *d_knn_ids,
+                                           uint64_t n_train, uint32_t knn_k, uint32_t M_sq, uint32_t M_pjbp, uint32_t *d_lists,
+                                           int device, void *cuda_stream) {
+    if (!d_base || !d_knn_ids || !d_lists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_projection_lists_device: null argument");
+    if (n == 0 || n >= (1ull << 31) || n_train == 0 || n_train * 2ull * M_pjbp >= (1ull << 32) || dim == 0 || dim % 8 != 0 ||
+        knn_k == 0 || M_sq == 0 || M_pjbp == 0 || M_pjbp > 64)
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_build_projection_lists_device: argument out of range");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    rg_graph g;
+    const rg_status s = rg::build::build_device(d_base, n, dim, metric, d_knn_ids, n_train, knn_k, M_sq, M_pjbp, 16, &g,
+                                                static_cast<cudaStream_t>(cuda_stream), d_lists);
+    cudaFree(g.d_adj);
+    return s;
+}
 }  // extern "C"

@@ -248,11 +248,6 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         ix->cfg_hash_space = value;
         return RG_OK;
     }
-    if (!strcmp(name, "stage_bufs")) {
-        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_bufs must be 0 (auto), 1 or 2");
-        ix->cfg_stage_bufs = value;
-        return RG_OK;
-    }
     if (!strcmp(name, "l2_hint")) {
         if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..3");
         ix->cfg_l2_hint = value;

@@ -40,7 +40,6 @@ struct rg_index {
 
     // tuning (0 = auto)
     int cfg_gather = 0, cfg_warps = 0, cfg_ctas = 0, cfg_stage_rows = 0, cfg_hash_log2 = 0, cfg_hash_space = 0;
-    int cfg_stage_bufs = 0;  // row staging buffers per warp (0 = auto = 1; 2: next batch in flight while one is scored)
     int cfg_l2_hint = 3, cfg_adj_prefetch = 3;  // see SearchParams::l2_hint / adj_prefetch; measured best on B200
                                                 // (profiles/r01_k1_variants_10m.txt)
 

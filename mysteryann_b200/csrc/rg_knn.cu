@@ -1051,15 +1051,20 @@ static uint64_t env_u64(const char *name, uint64_t dflt, uint64_t lo, uint64_t h
 //   conservative: tau = the k'-th best score seen so far.  Always certifiable, but the expected number of list insertions
 //                 at row i is k'/i: with k' = 150 the epilogue's hit path stays busy until ~1M rows have been seen, and a
 //                 1.25M-row shard (C4 on 8 GPUs) never gets out of it (round 1: 663 TFLOP/s per GPU against 1090 on one).
-//   optimistic  : tau = the r-th best score seen so far with r = clamp(ceil(c k' seen / n), r_min, k') - an estimate of
-//                 the (c k')-th best score of the WHOLE shard (rows in storage order are treated as a sample; c = 3,
-//                 r_min = 16).  Insertions drop to r/i per row, every block after the first few runs at the sparse
-//                 epilogue's speed, and the final list (~c k' entries) is cut to the k' best by the last select.  tau only
-//                 ever decreases, every non-survivor was rejected against a tau >= the final one, so the K3 certificate
-//                 (exact_K < tau - eps) is exactly as strong as before; what changes is that a query whose estimate was too
-//                 tight ends with too few survivors and FAILS the certificate.  Those queries are re-run with the
-//                 conservative schedule (and only what fails that goes to the exact FP32 scan), so the result is exact
-//                 for any row order - the row order only decides how many queries need the second pass.
+//   optimistic  : tau = the r-th best score seen so far with r << k' while few rows have been seen.  Rows in storage order
+//                 are treated as a sample: the r-th best of `seen` rows has expected rank r n / seen in the whole
+//                 shard, c_eff = r n / (seen k') times deeper than the k'-th best that is needed in the end.  r is the
+//                 smallest of 4, 8, 16, 32, ... whose c_eff still clears a safety factor (8, 4, 2.5, then 2: the rank
+//                 estimate of an r-th order statistic has a relative spread of 1/sqrt(r)), capped at k'.  Insertions
+//                 drop from k'/i to r/i per row - a 256-row first block, then a dozen hits per block until ~16K rows -
+//                 so every block after the first few runs at the sparse epilogue's speed, and the last select always
+//                 uses k' so that K3 re-scores k' survivors, not more.  tau only ever decreases and every non-survivor
+//                 was rejected against a tau >= the final one, so the K3 certificate (exact_K < tau - eps) is exactly
+//                 as strong as before; what changes is that a query whose estimate was too tight ends with too few
+//                 survivors and FAILS the certificate (expected: a few per 10^4 on rows in arbitrary order).  Those
+//                 queries are re-run with the conservative schedule (and only what fails that goes to the exact FP32
+//                 scan), so the result is exact for any row order - the order only decides how many queries need the
+//                 second pass.
 struct PassOutput {
     uint32_t *ids;
     float *dists;
@@ -1096,7 +1101,8 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
     const uint64_t q_batch = std::min<uint64_t>(env_u64("RG_KNN_QBATCH", 131072, 256, 1u << 20), (nq + 255) / 256 * 256);
     const uint64_t q_rows_pad = (q_batch + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
     const bool optimistic = env_u64("RG_KNN_OPTIMISTIC", 1, 0, 1) != 0;
-    const uint64_t r_min = env_u64("RG_KNN_RMIN", 16, 1, 256), c_safety = env_u64("RG_KNN_SAFETY", 3, 1, 6);
+    const uint64_t r_min = env_u64("RG_KNN_RMIN", 4, 1, 256);
+    const uint64_t first_rows = env_u64("RG_KNN_FIRST_ROWS", 256, 256, kCap) / kPairN * kPairN;
     int dev = 0, sms = 0, smem_max = 0;
     RG_CUDA_OK(cudaGetDevice(&dev));
     RG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1269,9 +1275,9 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
             gp.cand = cand;
             gp.cand_count = cand_count;
             gp.n_stages = n_stages;
-            // blocks [0,1024), then (growth-1) x everything seen so far (tau = +inf in the first block: every score of the
-            // first 1024 rows is kept, so the list can never overflow there)
-            uint64_t lo = 0, len = kCap;
+            // first block (256 rows optimistic, 1024 conservative), then (growth-1) x everything seen so far (tau = +inf in
+            // the first block: every score of its rows is kept, so the list can never overflow there)
+            uint64_t lo = 0, len = opt ? first_rows : uint64_t(kCap);
             while (lo < b_rows_pad) {
                 const uint64_t hi = std::min(b_rows_pad, lo + len);
                 gp.row_lo = lo;
@@ -1291,9 +1297,14 @@ rg_status knn_device(const float *d_base, uint64_t n, uint64_t id_base, const fl
                 // block always ends with the conservative k' so that K3 re-scores k' survivors, not c k'
                 uint32_t rank = kprime;
                 if (opt && hi < b_rows_pad) {
-                    const uint64_t seen = std::min<uint64_t>(hi, n);
-                    const uint64_t est = (c_safety * kprime * seen + n - 1) / n;
-                    rank = uint32_t(std::min<uint64_t>(kprime, std::max<uint64_t>(r_min, est)));
+                    const double seen = double(std::min<uint64_t>(hi, n));
+                    uint64_t r = r_min;
+                    for (; r < kprime; r *= 2) {
+                        const double c_eff = double(r) * double(n) / (seen * kprime);
+                        const double c_req = r < 8 ? 8.0 : (r < 16 ? 4.0 : (r < 32 ? 2.5 : 2.0));
+                        if (c_eff >= c_req) break;
+                    }
+                    rank = uint32_t(std::min<uint64_t>(kprime, r));
                 }
                 knn_select_kernel<<<(bq + 3) / 4, 128, 0, st>>>(cand, cand_count, thr, overflow, bq, rank);
                 launches += 2;

@@ -258,4 +258,43 @@ rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shard, uint
     return RG_OK;
 }
 
+// Host-buffer variant (what the compute_groundtruth driver calls from one thread per GPU): uploads the shard and the
+// queries, runs rg_knn_exact_sharded on a private stream, downloads this rank's slice of merged lists.
+rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, uint64_t id_base, const float *queries,
+                                    uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists,
+                                    void *nccl_comm, int rank, int world, int device) {
+    if (!base_shard || !queries || !ids || !dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact_sharded_host: null argument");
+    if (world <= 0 || rank < 0 || rank >= world) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact_sharded_host: bad rank/world");
+    if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    rg::DeviceGuard guard(device);
+    if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    uint64_t lo = 0, hi = 0;
+    rg_knn_sharded_slice(nq, rank, world, &lo, &hi);
+    struct Bufs {
+        float *base = nullptr, *q = nullptr, *d = nullptr;
+        uint32_t *i = nullptr;
+        cudaStream_t st = nullptr;
+        ~Bufs() {
+            cudaFree(base);
+            cudaFree(q);
+            cudaFree(d);
+            cudaFree(i);
+            if (st) cudaStreamDestroy(st);
+        }
+    } b;
+    RG_CUDA_OK(cudaStreamCreateWithFlags(&b.st, cudaStreamNonBlocking));
+    RG_CUDA_OK(cudaMalloc(&b.base, std::max<uint64_t>(n_shard, 1) * dim * sizeof(float)));
+    RG_CUDA_OK(cudaMalloc(&b.q, std::max<uint64_t>(nq, 1) * dim * sizeof(float)));
+    RG_CUDA_OK(cudaMalloc(&b.i, std::max<uint64_t>(hi - lo, 1) * K * sizeof(uint32_t)));
+    RG_CUDA_OK(cudaMalloc(&b.d, std::max<uint64_t>(hi - lo, 1) * K * sizeof(float)));
+    RG_CUDA_OK(cudaMemcpyAsync(b.base, base_shard, n_shard * dim * sizeof(float), cudaMemcpyHostToDevice, b.st));
+    RG_CUDA_OK(cudaMemcpyAsync(b.q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, b.st));
+    rg_status s = rg_knn_exact_sharded(b.base, n_shard, id_base, b.q, nq, dim, metric, K, b.i, b.d, nccl_comm, rank, world, device, b.st);
+    if (s != RG_OK) return s;
+    RG_CUDA_OK(cudaMemcpyAsync(ids, b.i, (hi - lo) * K * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.st));
+    RG_CUDA_OK(cudaMemcpyAsync(dists, b.d, (hi - lo) * K * sizeof(float), cudaMemcpyDeviceToHost, b.st));
+    RG_CUDA_OK(cudaStreamSynchronize(b.st));
+    return RG_OK;
+}
+
 }  // extern "C"

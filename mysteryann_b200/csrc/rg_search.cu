@@ -11,8 +11,8 @@
 //   3. filters the neighbours through an exact visited set (open-addressing hash, atomicCAS; by default a slab per CTA
 //      in global memory - 16-bit quotient entries when the id range allows, else 32-bit keys - optionally shared
 //      memory; replaces VisitedList's uint16 tag array)
-//   4. every warp gathers the rows of ITS surviving neighbours HBM -> shared memory (TMA bulk copies on mbarriers, two
-//      staging buffers per warp so that batch b+1 is in flight while batch b is scored; or cp.async)
+//   4. every warp gathers the rows of ITS surviving neighbours HBM -> shared memory (TMA bulk copies on an mbarrier, or
+//      cp.async) in batches of `stage_rows`
 //   5. and scores them 8 rows at a time, 4 lanes per row, in the exact FP32 operation order of the compiled
 //      reference distance (16 lane accumulators, unfused main loop, fused tails; distance.h:39-89,179-223);
 //      keys that cannot enter the pool (>= its last entry once full) are dropped on the spot
@@ -62,7 +62,6 @@ struct SearchParams {
     // slot is its top hash_log2 bits, the entry stores the remaining h16_rbits bits and the probe displacement
     uint32_t h16_bits, h16_rbits, h16_dbits, h16_maxd, h16_mult;
     uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
-    uint32_t stage_bufs;       // staging buffers per warp (1, or 2: the next batch is in flight while one is scored)
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
     uint32_t fallback;         // 1 = second pass over overflow_list with the big global table
@@ -77,7 +76,7 @@ struct SearchParams {
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
     uint32_t off_pool, off_cand, off_sorted, off_pos, off_ctrl, off_hash, off_warp;
-    uint32_t warp_bytes, woff_cid, woff_stage, stage_bytes;  // per-warp area: [2 mbarriers][candidate ids][row staging x bufs]
+    uint32_t warp_bytes, woff_cid, woff_stage;  // per-warp area: [mbarrier][candidate ids][row staging]
 };
 
 // ---- exact visited set --------------------------------------------------------------------------
@@ -139,9 +138,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     volatile uint32_t *s_ctrl = reinterpret_cast<volatile uint32_t *>(smem_raw + p.off_ctrl);
     uint32_t *s_ctrl_nv = reinterpret_cast<uint32_t *>(smem_raw + p.off_ctrl);
     unsigned char *wa = smem_raw + p.off_warp + size_t(warp) * p.warp_bytes;
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);  // [2]
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);
     uint32_t *s_cid = reinterpret_cast<uint32_t *>(wa + p.woff_cid);
-    unsigned char *s_stage_raw = wa + p.woff_stage;
+    float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
     uint32_t *hash32 = kHash == kHashShared ? reinterpret_cast<uint32_t *>(smem_raw + p.off_hash)
                                             : p.ghash + (size_t(blockIdx.x) << (kHash == kHashGlobal16 ? p.hash_log2 - 1 : p.hash_log2));
     unsigned short *hash16 = reinterpret_cast<unsigned short *>(hash32);
@@ -150,17 +149,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     const bool tail8 = (dim & 15u) != 0;
     const uint32_t cpr = dim >> 2;  // 16-byte chunks per row
     const uint32_t L = p.L, BR = p.stage_rows, RS = p.row_stride;
-    uint32_t mb_phase = 0;          // bit b = phase of this warp's mbarrier b
+    uint32_t mb_phase = 0;
     const bool rows_evict_first = (p.l2_hint & 1u) != 0;
     const bool pf_next = (p.adj_prefetch & 1u) != 0, pf_cand = (p.adj_prefetch & 2u) != 0;
     const uint64_t pol_first = l2_policy_evict_first();
     const uint32_t adj_row_bytes = p.adj_stride * 4u;
-    const bool two_bufs = kGather == 2 && p.stage_bufs == 2;
 
     if (kGather == 2) {
         if (lane == 0) {
-            mbar_init(&s_mbar[0], 1);
-            mbar_init(&s_mbar[1], 1);
+            mbar_init(s_mbar, 1);
             fence_mbar_init();
         }
     }
@@ -175,37 +172,27 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
     // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
     auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key) {
-        const uint32_t nb = (n + BR - 1) / BR;
-        auto issue = [&](uint32_t b) {  // TMA: batch b -> staging buffer b & 1 (or 0), completion on that buffer's mbarrier
-            const uint32_t buf = two_bufs ? (b & 1u) : 0u;
-            const uint32_t c0 = b * BR, rows = min(BR, n - c0);
-            float *stage = reinterpret_cast<float *>(s_stage_raw + size_t(buf) * p.stage_bytes);
-            if (lane == 0) mbar_arrive_expect_tx(&s_mbar[buf], rows * dim * 4u);
-            __syncwarp();
-            if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
-                for (uint32_t r = lane; r < rows; r += 32)
-                    bulk_g2s_hint(stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, &s_mbar[buf], pol_first);
-            } else {
-                for (uint32_t r = lane; r < rows; r += 32)
-                    bulk_g2s(stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, &s_mbar[buf]);
-            }
-        };
-        if (kGather == 2 && nb) issue(0);
-        for (uint32_t b = 0; b < nb; ++b) {
-            const uint32_t c0 = b * BR, rows = min(BR, n - c0);
-            const uint32_t buf = two_bufs ? (b & 1u) : 0u;
-            const float *stage = reinterpret_cast<const float *>(s_stage_raw + size_t(buf) * p.stage_bytes);
+        for (uint32_t c0 = 0; c0 < n; c0 += BR) {
+            const uint32_t rows = min(BR, n - c0);
+            const float *stage = s_stage;
             if (kGather == 2) {
-                if (two_bufs && b + 1 < nb) issue(b + 1);  // the other buffer was released by the __syncwarp of batch b-1
-                mbar_wait(&s_mbar[buf], (mb_phase >> buf) & 1u);
-                mb_phase ^= 1u << buf;
+                if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
+                __syncwarp();
+                if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
+                    for (uint32_t r = lane; r < rows; r += 32)
+                        bulk_g2s_hint(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar, pol_first);
+                } else {
+                    for (uint32_t r = lane; r < rows; r += 32)
+                        bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
+                }
+                mbar_wait(s_mbar, mb_phase);
+                mb_phase ^= 1u;
             } else {
                 const uint32_t total = rows * cpr;
-                float *st = const_cast<float *>(stage);
                 for (uint32_t idx = lane; idx < total; idx += 32) {
                     const uint32_t r = __umulhi(idx, p.chunk_magic);
                     const uint32_t c = idx - r * cpr;
-                    cp_async16(st + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
+                    cp_async16(s_stage + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -232,8 +219,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     if (keep) s_cand[pos0 + __popc(m & lanemask_lt())] = key;
                 }
             }
-            __syncwarp();  // all reads of this staging buffer done before another batch lands in it
-            if (kGather == 2 && !two_bufs && b + 1 < nb) issue(b + 1);
+            __syncwarp();  // all reads of the staging buffer done before the next batch lands in it
         }
     };
 
@@ -592,7 +578,6 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.stage_rows = ix->cfg_stage_rows ? uint32_t(ix->cfg_stage_rows) : 8u;
     g->gather = ix->cfg_gather ? ix->cfg_gather : 2;
     if (build) g->gather = 2;
-    p.stage_bufs = (g->gather == 2 && ix->cfg_stage_bufs == 2) ? 2u : 1u;
     g->warps = ix->cfg_warps ? ix->cfg_warps : 2;  // measured best on B200 (profiles/r01_k1_v2_sweep.txt)
     if (warps_override) g->warps = warps_override;
     const uint32_t W = uint32_t(g->warps);
@@ -643,8 +628,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     const uint32_t cid_cap = round_up((ix->adj_stride - 1 + W - 1) / W, 8);
     p.woff_cid = 16;
     p.woff_stage = round_up(16 + cid_cap * 4, 128);
-    p.stage_bytes = round_up(p.stage_rows * p.row_stride * 4, 128);
-    p.warp_bytes = p.woff_stage + p.stage_bufs * p.stage_bytes;
+    p.warp_bytes = p.woff_stage + round_up(p.stage_rows * p.row_stride * 4, 128);
     off += W * p.warp_bytes;
     g->smem_bytes = off;
     if (size_t(off) > size_t(ix->max_smem_optin))
@@ -731,36 +715,17 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     Geometry g1, g2;
     rg_status s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
-    // Primary pass.  Automatic mode picks, in this order of preference (same-box A/B in profiles/r02_k1_ab_*.txt):
-    //   two warps per query, 32-bit hash keys    when the slabs of all resident queries fit the persisting part of L2
-    //   two warps per query, 16-bit quotients    when only the half-size slabs fit (the 16-bit CAS is a little slower
-    //                                            than the 32-bit one while both hit L2, but far faster than probing HBM)
-    //   four warps per query (half the residents), 32-bit then 16-bit, when that makes the slabs fit
-    //   two warps per query, 16-bit quotients    otherwise (nothing fits: at least halve the hash traffic)
-    const bool auto_hash = ix->cfg_hash_space == 0, auto_warps = ix->cfg_warps == 0;
-    auto fits = [&](const Geometry &g) {
-        const uint64_t cap = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g.ctas_per_sm);
-        return g.slab_bytes == 0 || persisting_window_fits(ix, cap * g.slab_bytes);
-    };
+    // Primary pass, automatic mode (same-box sweeps in profiles/r02_k1_sweep_*.txt): two warps per query; 32-bit hash keys
+    // while the slabs of all resident queries fit the persisting part of L2 (0.87 vs 0.84 of the HBM peak at L_pq = 55:
+    // the 16-bit CAS is a little slower while both hit L2), 16-bit quotient entries - half the slab - beyond that (0.75-0.79
+    // vs 0.71 at L_pq = 100, 0.64 vs 0.57 at 200, a tie at 500).  Four warps per query, which round 1 used to make 32-bit
+    // slabs fit at L_pq ~ 100, no longer pays: halving the resident queries costs more than the L2 hits return.
+    const bool auto_hash = ix->cfg_hash_space == 0;
     s = make_geometry(ix, k, L, false, build, &g1, 0, !auto_hash);
     if (s != RG_OK) return s;
-    if ((auto_hash || auto_warps) && (ix->cfg_l2_hint & 2) && !fits(g1)) {
-        bool done = false;
-        for (int w : {0, 4}) {
-            if (w && (!auto_warps || build)) break;
-            for (int h16 = (w == 0 ? 1 : 0); h16 < 2 && !done; ++h16) {
-                if (h16 && !auto_hash) continue;
-                Geometry g;
-                if (make_geometry(ix, k, L, false, build, &g, w, auto_hash ? h16 != 0 : true) != RG_OK) continue;
-                if (h16 && g.hash_kind != kHashGlobal16) continue;
-                if (fits(g)) {
-                    g1 = g;
-                    done = true;
-                }
-            }
-            if (done) break;
-        }
-        if (!done && auto_hash) {
+    if (auto_hash && g1.slab_bytes) {
+        const uint64_t cap = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm);
+        if (!persisting_window_fits(ix, cap * g1.slab_bytes)) {
             Geometry g;
             if (make_geometry(ix, k, L, false, build, &g, 0, true) == RG_OK) g1 = g;
         }

@@ -102,7 +102,7 @@ void check(rg_status s, const char *what) {
 
 template <typename T>
 int aux_main(const std::string &base_file, const std::string &query_file, const std::string &gt_file, uint64_t k, int metric,
-             bool cosine, const std::string &tags_file, int n_devices, uint64_t part_rows) {
+             bool cosine, const std::string &tags_file, int n_devices, uint64_t part_rows, bool explicit_parts) {
     const BinHeader bh = read_header(base_file), qh = read_header(query_file);
     std::cout << "Reading bin file " << base_file << " ...\n#pts = " << bh.npts << ", #dims = " << bh.ndims << std::endl;
     if (bh.ndims != qh.ndims) throw std::runtime_error("base and query dimensions differ");
@@ -136,7 +136,49 @@ int aux_main(const std::string &base_file, const std::string &query_file, const 
               << " dimensions using" << (metric == RG_METRIC_INNER_PRODUCT ? " MIPS " : cosine ? " Cosine " : " L2 ")
               << "distance fn. on " << n_devices << " GPU(s)" << std::endl;
 
+    std::vector<uint32_t> closest_points(nqueries * k);
+    std::vector<float> dist_closest_points(nqueries * k);
+
+    // Several GPUs, default part size, no tags: ONE base shard per GPU and the merge on the devices (rg_knn_exact_sharded:
+    // K2/K3 per shard, grouped ncclSend/ncclRecv exchange of the per-shard lists over NVLink, K4) instead of the
+    // part-by-part walk with a host-side merge below.  One host thread per GPU, communicators from ncclCommInitAll.
+    const bool sharded = n_devices > 1 && location_to_tag.empty() && !explicit_parts && bh.npts >= uint64_t(n_devices) &&
+                         uint64_t(n_devices) * k <= 1024 && (bh.npts / n_devices + 1) * dpad * sizeof(float) <= (64ull << 30);
+    if (sharded) {
+        std::vector<void *> comms(size_t(n_devices), nullptr);
+        check(rg_nccl_comm_init_all(comms.data(), n_devices, nullptr), "rg_nccl_comm_init_all");
+        std::cout << "Base sharded over " << n_devices << " GPUs, per-shard lists exchanged with NCCL " << rg_nccl_version()
+                  << " and merged on the devices" << std::endl;
+        std::mutex err_mu;
+        std::string err;
+        auto worker = [&](int dev) {
+            try {
+                const uint64_t q = bh.npts / n_devices, r = bh.npts % n_devices;
+                const uint64_t start_id = uint64_t(dev) * q + std::min<uint64_t>(dev, r), npoints = q + (uint64_t(dev) < r ? 1 : 0);
+                std::vector<float> base;
+                load_part_as_float<T>(base_file, start_id, npoints, ndims, dpad, base);
+                if (cosine) normalize_rows(base, npoints, ndims, dpad);
+                uint64_t lo = 0, hi = 0;
+                rg_knn_sharded_slice(nqueries, dev, n_devices, &lo, &hi);
+                check(rg_knn_exact_sharded_host(base.data(), npoints, start_id, queries.data(), nqueries, uint32_t(dpad), metric,
+                                                uint32_t(k), closest_points.data() + lo * k, dist_closest_points.data() + lo * k,
+                                                comms[size_t(dev)], dev, n_devices, dev),
+                      "rg_knn_exact_sharded_host");
+            } catch (const std::exception &ex) {
+                std::lock_guard<std::mutex> lock(err_mu);
+                if (err.empty()) err = ex.what();
+            }
+        };
+        std::vector<std::thread> threads;
+        for (int d = 1; d < n_devices; ++d) threads.emplace_back(worker, d);
+        worker(0);
+        for (auto &t : threads) t.join();
+        for (void *c : comms) rg_nccl_comm_destroy(c);
+        if (!err.empty()) throw std::runtime_error(err);
+    }
+
     // per-part lists, [part][nq][k]; empty slots carry kNoId
+    if (!sharded) {
     std::vector<uint32_t> part_ids(num_parts * nqueries * k, kNoId);
     std::vector<float> part_dists(num_parts * nqueries * k, 0.f);
     std::mutex err_mu;
@@ -171,8 +213,6 @@ int aux_main(const std::string &base_file, const std::string &query_file, const 
     if (!err.empty()) throw std::runtime_error(err);
 
     // merge (:424-448): K4 takes up to 1024 / k lists at a time; more parts are folded group by group
-    std::vector<uint32_t> closest_points(nqueries * k);
-    std::vector<float> dist_closest_points(nqueries * k);
     const uint64_t group = std::max<uint64_t>(2, 1024 / k);
     uint64_t done = 0;
     bool have_acc = false;
@@ -199,6 +239,7 @@ int aux_main(const std::string &base_file, const std::string &query_file, const 
         have_acc = true;
         done += take;
     }
+    }  // !sharded
     for (uint64_t i = 0; i < nqueries; ++i) {
         bool short_list = false;
         for (uint64_t j = 0; j < k; ++j) {
@@ -222,6 +263,7 @@ int main(int argc, char **argv) {
     std::string data_type, dist_fn, base_file, query_file, gt_file, tags_file;
     uint64_t K = 0, part_rows = kPartSize;
     int devices = 0;
+    bool explicit_parts = false;
     try {
         CliArgs args(argc, argv, {{"-h", "--help"}});
         if (args.has("help")) {
@@ -238,6 +280,7 @@ int main(int argc, char **argv) {
         tags_file = args.get<std::string>("tags_file", std::string());
         devices = args.get<int>("devices", 0);
         part_rows = args.get<uint64_t>("part_size", kPartSize);
+        explicit_parts = args.has("part_size");
     } catch (const std::exception &ex) {
         std::cerr << ex.what() << '\n';
         return -1;
@@ -273,9 +316,9 @@ int main(int argc, char **argv) {
     try {
         auto t0 = std::chrono::steady_clock::now();
         int rc;
-        if (data_type == "float") rc = aux_main<float>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows);
-        else if (data_type == "int8") rc = aux_main<int8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows);
-        else rc = aux_main<uint8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows);
+        if (data_type == "float") rc = aux_main<float>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
+        else if (data_type == "int8") rc = aux_main<int8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
+        else rc = aux_main<uint8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
         std::cout << "Total time: " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;
         return rc;
     } catch (const std::exception &e) {

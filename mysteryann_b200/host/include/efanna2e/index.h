@@ -17,6 +17,7 @@ class Index {
     size_t GetSizeOfDataset() const { return nd_; }
     const float *GetBasePointSet() const { return data_bp_; }
     const float *GetSampledQuerySet() const { return data_sq_; }
+    const Distance *GetDistance() const { return distance_; }
 
    protected:
     const size_t dimension_;

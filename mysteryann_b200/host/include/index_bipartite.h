@@ -4,6 +4,7 @@
 // the host CPU like the reference (edge-identical at one thread) or, with Parameters "gpu_build" = 1, on the GPU.  The legacy bipartite methods of the reference are out of scope.
 #pragma once
 #include <cstdint>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -38,7 +39,9 @@ class IndexBipartite : public Index {
     // ---- search (src/index_bipartite.cpp:2311-2420) ----
     // Kept for API parity: the GPU path needs no visited-list pool; this uploads the index to the device.
     void InitVisitedListPool(uint32_t num_threads);
-    // One query = a batch of one (parameters must hold "L_pq").  Returns {cmps, hops}.
+    // One query (parameters must hold "L_pq").  Returns {cmps, hops}.  Re-entrant like the reference's: concurrent callers
+    // are micro-batched into one GPU launch (see PendingQuery below); a lone caller pays a launch + sync per query, so
+    // batch callers should use SearchRoarGraphBatch.
     std::pair<uint32_t, uint32_t> SearchRoarGraph(const float *query, size_t k, size_t &qid,
                                                   const Parameters &parameters, unsigned *indices,
                                                   std::vector<float> &res_dists);
@@ -53,6 +56,9 @@ class IndexBipartite : public Index {
 
     CompactGraph &GetProjectionGraph() { return projection_graph_; }
     std::vector<std::vector<uint32_t>> &GetLearnBaseKNN() { return learn_base_knn_; }
+    // the pruned pivot list one training query produces in P1 of LinkProjection (test hook, see index_bipartite.cpp)
+    static std::vector<uint32_t> PivotProjectionList(const float *base, size_t dim, const Distance *dist, uint32_t M_pjbp,
+                                                     const uint32_t *nn, size_t n_nn);
     uint32_t GetProjectionEp() const { return projection_ep_; }
     void SetProjectionGraph(uint32_t ep, CompactGraph graph);  // adopt an externally built graph
     void SetBaseData(const float *base, size_t n);             // adopt caller-owned padded rows
@@ -82,6 +88,32 @@ class IndexBipartite : public Index {
     int device_ = 0, device_count_ = 1;
     std::mutex device_mutex_;
     std::mutex search_mutex_;  // the GPU replicas own one set of scratch buffers each: concurrent callers take turns
+
+    // Micro-batching of concurrent SearchRoarGraph callers (the reference's OpenMP loop, tests/test_search_roargraph.cpp:
+    // 203-209, kept as is by a caller): the first caller to arrive leads - it waits microbatch_us_ for others, packs every
+    // pending query with the same (k, L_pq) into ONE rg_search_batch launch and hands the results back.
+    struct PendingQuery {
+        const float *query;
+        size_t k;
+        uint32_t L;
+        unsigned *indices;
+        float *dists;
+        uint32_t cmps = 0, hops = 0;
+        bool done = false, short_result = false;
+        std::string error;
+    };
+    void lead_microbatch(std::unique_lock<std::mutex> &lk);
+    std::mutex mb_mutex_;
+    std::condition_variable mb_cv_;
+    std::vector<PendingQuery *> mb_pending_;
+    bool mb_leader_active_ = false;
+    int microbatch_us_ = 50;             // RG_MICROBATCH_US; 0 = every call is its own batch of one
+    float *mb_queries_ = nullptr;        // page-locked staging (queries in, results out) for up to kMicrobatchMax queries
+    unsigned *mb_ids_ = nullptr;
+    float *mb_dists_ = nullptr;
+    uint32_t *mb_cmps_ = nullptr, *mb_hops_ = nullptr;
+    size_t mb_k_cap_ = 0;
+    static constexpr size_t kMicrobatchMax = 4096;
 };
 
 }  // namespace efanna2e

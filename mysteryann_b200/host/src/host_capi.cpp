@@ -51,13 +51,37 @@ __attribute__((visibility("default"))) int rgh_build_index(const float *base, ui
     }
 }
 
+// P1 lists of the host build (PruneBiSearchBaseGetBase per training query): out [n_train][M_pjbp + 1], word 0 = length.
+__attribute__((visibility("default"))) int rgh_projection_lists(const float *base, uint32_t dim, int metric, const uint32_t *knn_ids,
+                                                                 uint64_t n_train, uint32_t knn_k, uint32_t M_sq, uint32_t M_pjbp,
+                                                                 uint32_t *out) {
+    try {
+        efanna2e::IndexBipartite index(dim, 1, static_cast<efanna2e::Metric>(metric), nullptr);
+        const efanna2e::Distance *dist = index.GetDistance();
+        const size_t take = std::min<size_t>(knn_k, M_sq);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t i = 0; i < (int64_t)n_train; ++i) {
+            const std::vector<uint32_t> l =
+                efanna2e::IndexBipartite::PivotProjectionList(base, dim, dist, M_pjbp, knn_ids + (size_t)i * knn_k, take);
+            uint32_t *row = out + (size_t)i * (M_pjbp + 1);
+            row[0] = (uint32_t)l.size();
+            for (size_t j = 0; j < l.size(); ++j) row[1 + j] = l[j];
+            for (size_t j = l.size(); j < M_pjbp; ++j) row[1 + j] = 0;
+        }
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return 1;
+    }
+}
+
 // The reference driver's own search loop (tests/test_search_roargraph.cpp:160-209) on files: load base + index, then ONE
 // SearchRoarGraph CALL PER QUERY from num_threads OpenMP threads (schedule(dynamic,1)) - the way existing callers of the
 // reference use the class.  queries: nq padded rows.  Outputs: ids/dists [nq*k], cmps/hops [nq].
 __attribute__((visibility("default"))) int rgh_search_per_query(const char *base_fbin, const char *index_file, int metric,
                                                                  const float *queries, uint64_t nq, uint32_t k, uint32_t L_pq,
                                                                  uint32_t num_threads, uint32_t *ids, float *dists,
-                                                                 uint32_t *cmps, uint32_t *hops) {
+                                                                 uint32_t *cmps, uint32_t *hops, double *loop_seconds) {
     try {
         Mute mute(true);
         uint32_t base_num = 0, base_dim = 0;
@@ -70,6 +94,18 @@ __attribute__((visibility("default"))) int rgh_search_per_query(const char *base
         efanna2e::Parameters p;
         p.Set<uint32_t>("L_pq", L_pq);
         std::string first_error;
+        {   // warm-up like the reference's first 100 sequential queries (tests/test_search_roargraph.cpp:198-200)
+            size_t qid = 0;
+            std::vector<float> res_dists(k);
+            std::vector<unsigned> tmp(k);
+            for (uint64_t i = 0; i < std::min<uint64_t>(nq, 8); ++i) {
+                try {
+                    index.SearchRoarGraph(queries + (size_t)i * dim, k, qid, p, tmp.data(), res_dists);
+                } catch (const std::exception &) {
+                }
+            }
+        }
+        const auto t0 = std::chrono::high_resolution_clock::now();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
         for (int64_t i = 0; i < (int64_t)nq; ++i) {
             try {
@@ -84,6 +120,7 @@ __attribute__((visibility("default"))) int rgh_search_per_query(const char *base
                 if (first_error.empty()) first_error = ex.what();
             }
         }
+        if (loop_seconds) *loop_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         if (!first_error.empty()) {
             g_err = first_error;
             return 1;

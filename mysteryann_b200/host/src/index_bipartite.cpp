@@ -12,6 +12,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 #include <fstream>
 #include <limits>
 #include <sstream>
@@ -41,9 +44,17 @@ Index::~Index() { delete distance_; }
 IndexBipartite::IndexBipartite(size_t dimension, size_t n, Metric m, Index *initializer)
     : Index(dimension, n, m), initializer_(initializer) {
     if (m == COSINE) need_normalize = true;  // :30-38
+    if (const char *e = std::getenv("RG_MICROBATCH_US")) microbatch_us_ = std::max(0, atoi(e));
 }
 
-IndexBipartite::~IndexBipartite() { release_device(); }
+IndexBipartite::~IndexBipartite() {
+    release_device();
+    for (void *p : {(void *)mb_queries_, (void *)mb_ids_, (void *)mb_dists_, (void *)mb_cmps_, (void *)mb_hops_})
+        if (p) {
+            rg_host_unregister(p);
+            free(p);
+        }
+}
 
 namespace {
 [[noreturn]] void throw_rg(const char *what) {
@@ -231,13 +242,106 @@ void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_
     }
 }
 
+// Leader side of the micro-batch (mb_mutex_ held on entry and on return): wait a moment for more callers, then run every
+// pending query that shares (k, L_pq) with the oldest one as ONE batch.
+void IndexBipartite::lead_microbatch(std::unique_lock<std::mutex> &lk) {
+    if (microbatch_us_ > 0 && mb_pending_.size() < kMicrobatchMax) {
+        lk.unlock();
+        std::this_thread::sleep_for(std::chrono::microseconds(microbatch_us_));
+        lk.lock();
+    }
+    if (mb_pending_.empty()) return;
+    const size_t k = mb_pending_.front()->k;
+    const uint32_t L = mb_pending_.front()->L;
+    std::vector<PendingQuery *> batch, rest;
+    for (PendingQuery *q : mb_pending_) (q->k == k && q->L == L && batch.size() < kMicrobatchMax ? batch : rest).push_back(q);
+    mb_pending_.swap(rest);
+    lk.unlock();
+    const size_t nb = batch.size(), dim = dimension_;
+    std::string error;
+    try {
+        auto pinned = [&](auto *&ptr, size_t count) {  // page-locked once: rg_search_batch then works on it in place
+            using T = std::remove_reference_t<decltype(*ptr)>;
+            void *raw = nullptr;
+            if (posix_memalign(&raw, 4096, count * sizeof(T)) != 0) throw std::bad_alloc();
+            ptr = static_cast<T *>(raw);
+            (void)rg_host_register(ptr, count * sizeof(T));  // failure only means the staged path is taken
+        };
+        if (!mb_queries_) {
+            pinned(mb_queries_, kMicrobatchMax * dim);
+            pinned(mb_cmps_, kMicrobatchMax);
+            pinned(mb_hops_, kMicrobatchMax);
+        }
+        if (mb_k_cap_ < k) {
+            for (void *p : {(void *)mb_ids_, (void *)mb_dists_})
+                if (p) {
+                    rg_host_unregister(p);
+                    free(p);
+                }
+            mb_ids_ = nullptr;
+            mb_dists_ = nullptr;
+            pinned(mb_ids_, kMicrobatchMax * k);
+            pinned(mb_dists_, kMicrobatchMax * k);
+            mb_k_cap_ = k;
+        }
+        for (size_t i = 0; i < nb; ++i) memcpy(mb_queries_ + i * dim, batch[i]->query, dim * sizeof(float));
+        if (!device_index_) upload_to_device();
+        rg_status s;
+        {
+            std::lock_guard<std::mutex> serial(search_mutex_);
+            s = rg_search_batch(device_index_, mb_queries_, nb, (uint32_t)k, L, mb_ids_, mb_dists_, mb_cmps_, mb_hops_);
+        }
+        if (s != RG_OK && s != RG_ERR_NOT_ENOUGH_RESULTS) throw_rg("rg_search_batch");
+        const std::string short_msg = s == RG_ERR_NOT_ENOUGH_RESULTS ? rg_last_error_string() : "";
+        for (size_t i = 0; i < nb; ++i) {
+            PendingQuery *q = batch[i];
+            memcpy(q->indices, mb_ids_ + i * k, k * sizeof(unsigned));
+            memcpy(q->dists, mb_dists_ + i * k, k * sizeof(float));
+            q->cmps = mb_cmps_[i];
+            q->hops = mb_hops_[i];
+            // a query that ended with fewer than k pool entries has its ids filled with 0xFFFFFFFF: only ITS caller gets the
+            // reference's "not enough results" exception (:2408-2412)
+            if (s == RG_ERR_NOT_ENOUGH_RESULTS && k > 0 && mb_ids_[i * k + k - 1] == 0xFFFFFFFFu) {
+                q->short_result = true;
+                q->error = short_msg;
+            }
+        }
+    } catch (const std::exception &ex) {
+        error = ex.what();
+    }
+    lk.lock();
+    for (PendingQuery *q : batch) {
+        if (!error.empty()) q->error = error;
+        q->done = true;
+    }
+}
+
 std::pair<uint32_t, uint32_t> IndexBipartite::SearchRoarGraph(const float *query, size_t k, size_t &,
                                                               const Parameters &parameters, unsigned *indices,
                                                               std::vector<float> &res_dists) {
-    uint32_t cmps = 0, hops = 0;
     if (res_dists.size() < k) res_dists.resize(k);
-    SearchRoarGraphBatch(query, 1, k, parameters, indices, res_dists.data(), &cmps, &hops);
-    return {cmps, hops};
+    PendingQuery me;
+    me.query = query;
+    me.k = k;
+    me.L = parameters.Get<uint32_t>("L_pq");
+    me.indices = indices;
+    me.dists = res_dists.data();
+    {
+        std::unique_lock<std::mutex> lk(mb_mutex_);
+        mb_pending_.push_back(&me);
+        while (!me.done) {
+            if (!mb_leader_active_) {  // nobody is collecting: lead one batch (mine, unless an older (k, L) group goes first)
+                mb_leader_active_ = true;
+                lead_microbatch(lk);
+                mb_leader_active_ = false;
+                mb_cv_.notify_all();
+            } else {
+                mb_cv_.wait(lk);
+            }
+        }
+    }
+    if (!me.error.empty()) throw std::runtime_error(me.error);
+    return {me.cmps, me.hops};
 }
 
 // ====================================================================================================
@@ -353,6 +457,20 @@ std::vector<uint32_t> prune_base_search(const BuildCtx &c, std::vector<Neighbor>
 }
 
 }  // namespace
+
+// P1 of LinkProjection for ONE training query (:1059-1084 + PruneBiSearchBaseGetBase): nn = its learn->base list (already
+// cut to M_sq), element 0 the pivot.  Exposed so that the GPU build's projection prune can be checked list by list.
+std::vector<uint32_t> IndexBipartite::PivotProjectionList(const float *base, size_t dim, const Distance *dist, uint32_t M_pjbp,
+                                                          const uint32_t *nn, size_t n_nn) {
+    if (n_nn == 0) return {};
+    const BuildCtx c{base, dim, dist, M_pjbp};
+    const uint32_t pivot = nn[0];
+    std::vector<Neighbor> pool;
+    pool.reserve(n_nn);
+    for (size_t i = 0; i < n_nn; ++i)
+        if (nn[i] != pivot) pool.emplace_back(nn[i], c.d(nn[i], pivot), false);
+    return prune_projection(c, pool, pivot);
+}
 
 // CalculateProjectionep, :2004-2041: centroid in FP32 (row order), squared L2 to it, first minimum.
 void IndexBipartite::calculate_projection_ep() {

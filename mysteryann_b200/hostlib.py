@@ -30,8 +30,23 @@ def lib():
                                          C.c_char_p, C.c_int, C.c_void_p]
         _lib.rgh_search_per_query.restype = C.c_int
         _lib.rgh_search_per_query.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
-                                              C.c_uint32] + [C.c_void_p] * 4
+                                              C.c_uint32] + [C.c_void_p] * 5
+        _lib.rgh_projection_lists.restype = C.c_int
+        _lib.rgh_projection_lists.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_void_p]
     return _lib
+
+
+def projection_lists(base, knn_ids, metric=1, M_sq=100, M_pjbp=35):
+    """P1 of the host build: the pruned pivot list of every training query, uint32 [n_train, M_pjbp + 1] (column 0 = length)."""
+    base = np.ascontiguousarray(base, np.float32)
+    knn_ids = np.ascontiguousarray(knn_ids, np.uint32)
+    out = np.zeros((knn_ids.shape[0], M_pjbp + 1), np.uint32)
+    rc = lib().rgh_projection_lists(base.ctypes.data, base.shape[1], metric, knn_ids.ctypes.data, knn_ids.shape[0],
+                                    knn_ids.shape[1], M_sq, M_pjbp, out.ctypes.data)
+    if rc:
+        raise RuntimeError(lib().rgh_last_error().decode())
+    return out
 
 
 def build_index(base, train, knn_ids, out_path, metric=1, M_sq=100, M_pjbp=35, L_pjpq=500, threads=1, quiet=True):
@@ -51,7 +66,8 @@ def build_index(base, train, knn_ids, out_path, metric=1, M_sq=100, M_pjbp=35, L
 
 def search_per_query(base_fbin, index_file, queries, k, L_pq, metric=1, threads=8):
     """The reference driver's loop on the drop-in class: one IndexBipartite::SearchRoarGraph call per query from `threads`
-    OpenMP threads (each call is a GPU batch of one).  Returns dict(ids, dists, cmps, hops)."""
+    OpenMP threads (concurrent callers are micro-batched into one GPU launch inside the class).  Returns dict(ids, dists, cmps,
+    hops, seconds = wall time of the loop)."""
     queries = np.ascontiguousarray(queries, np.float32)
     nq = queries.shape[0]
     assert queries.shape[1] % 8 == 0
@@ -59,8 +75,10 @@ def search_per_query(base_fbin, index_file, queries, k, L_pq, metric=1, threads=
     dists = np.empty((nq, k), np.float32)
     cmps = np.empty(nq, np.uint32)
     hops = np.empty(nq, np.uint32)
+    sec = C.c_double(0)
     rc = lib().rgh_search_per_query(str(base_fbin).encode(), str(index_file).encode(), metric, queries.ctypes.data, nq, k,
-                                    L_pq, threads, ids.ctypes.data, dists.ctypes.data, cmps.ctypes.data, hops.ctypes.data)
+                                    L_pq, threads, ids.ctypes.data, dists.ctypes.data, cmps.ctypes.data, hops.ctypes.data,
+                                    C.byref(sec))
     if rc:
         raise RuntimeError(lib().rgh_last_error().decode())
-    return dict(ids=ids, dists=dists, cmps=cmps, hops=hops)
+    return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, seconds=sec.value)

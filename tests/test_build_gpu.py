@@ -74,3 +74,23 @@ def test_gpu_build_matches_cpu_build_quality(capi, metric, n, dim, M_sq, M, L_bu
     for x in (ix_gpu, ix_cpu, ix_dl):
         x.close()
     g.close()
+
+
+@pytest.mark.parametrize("metric,n,dim,M_sq,M", [(1, 20000, 200, 100, 35), (0, 6000, 104, 40, 14), (1, 3000, 512, 64, 24)])
+def test_projection_lists_equal_host(capi, metric, n, dim, M_sq, M):
+    """P1 of the build (pivot projection + PruneBiSearchBaseGetBase, src/index_bipartite.cpp:1059-1097, 1612-1694) is
+    deterministic given the kNN file: the GPU prune kernel's list of EVERY training query must equal the host restatement's
+    (which is byte-identical to the reference at -T 1) - same ids, same order, same length."""
+    import torch
+    from mysteryann_b200 import hostlib, synth
+
+    base, train, _ = synth.make_numpy(n, n, 10, dim, seed=3 * n + dim, normalize=(dim == 512))
+    knn, _ = capi.knn_exact(base, train, M_sq, metric=metric)
+    want = hostlib.projection_lists(base, knn, metric=metric, M_sq=M_sq, M_pjbp=M)
+    got = capi.projection_lists_device(torch.from_numpy(base).cuda(), torch.from_numpy(knn.view(np.int32)).cuda(), M_sq=M_sq,
+                                       M_pjbp=M, metric=metric).cpu().numpy().view(np.uint32)
+    assert (got[:, 0] == want[:, 0]).all(), np.argwhere(got[:, 0] != want[:, 0])[:5]
+    assert want[:, 0].max() <= M and want[:, 0].min() >= 1
+    mask = np.arange(1, M + 1)[None, :] <= want[:, :1]
+    bad = np.argwhere((got[:, 1:] != want[:, 1:]) & mask)
+    assert len(bad) == 0, (len(bad), bad[:5], got[bad[0][0]], want[bad[0][0]])

@@ -56,6 +56,29 @@ def test_compute_groundtruth_parts_and_format(bins, oracle, tmp_path, dist_fn, m
     check_knn(ids, dists, want_ids, want_d, f"cli {dist_fn}")
 
 
+def test_compute_groundtruth_two_gpus_nccl(bins, oracle, tmp_path):
+    """--devices 2 without --part_size: one base shard per GPU, rg_knn_exact_sharded_host from one thread per GPU (NCCL
+    exchange + K4 merge on the devices).  Skipped on a one-GPU box."""
+    import torch
+
+    from mysteryann_b200 import io
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(31)
+    base = rng.standard_normal((9001, 96)).astype(np.float32)
+    q = rng.standard_normal((333, 96)).astype(np.float32)
+    io.write_fbin(tmp_path / "base.fbin", base)
+    io.write_fbin(tmp_path / "q.fbin", q)
+    out = run([os.path.join(bins, "compute_groundtruth"), "--data_type", "float", "--dist_fn", "l2", "--base_file",
+               str(tmp_path / "base.fbin"), "--query_file", str(tmp_path / "q.fbin"), "--gt_file", str(tmp_path / "gt.bin"),
+               "--K", "25", "--devices", "2"])
+    assert "Base sharded over 2 GPUs" in out
+    ids, dists = io.read_ibin(tmp_path / "gt.bin")
+    want_ids, want_d, _ = oracle.exact_knn(base, q, 25, metric=0)
+    check_knn(ids, dists, want_ids, want_d, "cli 2 gpus")
+
+
 def test_compute_groundtruth_cosine_and_uint8(bins, tmp_path):
     """cosine = L2 on normalised rows (compute_groundtruth.cpp:146-175); uint8 input is converted like load_bin_as_float."""
     from mysteryann_b200 import io
@@ -256,7 +279,8 @@ def test_search_driver_rejects_foreign_index(bins, tmp_path):
 def test_per_query_api_from_openmp_threads(tmp_path):
     """Existing callers of the reference call IndexBipartite::SearchRoarGraph once per query from OpenMP threads
     (tests/test_search_roargraph.cpp:203-209).  The drop-in class must give the reference's answers that way too
-    (each call is a GPU batch of one; concurrent callers are serialised inside the class)."""
+    (concurrent callers are micro-batched into one GPU launch inside the class; RG_MICROBATCH_US=0 makes every call its own
+    batch of one)."""
     from conftest import load_case
     from mysteryann_b200 import hostlib, io
 
@@ -264,8 +288,12 @@ def test_per_query_api_from_openmp_threads(tmp_path):
     c = load_case("ip_d200")
     io.write_fbin(tmp_path / "base.fbin", c["base"])
     io.write_index(tmp_path / "g.index", c["ep"], c["offsets"], c["adj"])
-    for L in (10, 32):
-        got = hostlib.search_per_query(tmp_path / "base.fbin", tmp_path / "g.index", c["test"], 10, L, metric=1, threads=8)
-        for key in ("ids", "cmps", "hops"):
-            assert (got[key] == c[f"{key}_{L}"]).all(), (key, L)
-        assert (got["dists"].view(np.uint32) == c[f"dists_{L}"].view(np.uint32)).all()
+    for window in ("50", "0"):
+        os.environ["RG_MICROBATCH_US"] = window
+        for L in (10, 32):
+            got = hostlib.search_per_query(tmp_path / "base.fbin", tmp_path / "g.index", c["test"], 10, L, metric=1, threads=8)
+            for key in ("ids", "cmps", "hops"):
+                assert (got[key] == c[f"{key}_{L}"]).all(), (key, L, window)
+            assert (got["dists"].view(np.uint32) == c[f"dists_{L}"].view(np.uint32)).all()
+            print(f"per-query API, 8 threads, window {window} us, L={L}: {len(c['test']) / got['seconds']:.0f} queries/s")
+    del os.environ["RG_MICROBATCH_US"]

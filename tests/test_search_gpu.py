@@ -41,16 +41,14 @@ def capi():
 
 # (gather, warps per query, visited-hash space, L2 hints, adjacency prefetch): cp.async / TMA bulk gathers, 1..8 warps per
 # query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch
-# hash space: 1 shared memory, 2 global 32-bit keys, 3 global 16-bit quotient entries, 0 auto (= 3 where the id range allows);
-# a sixth field, when present, is the number of row staging buffers per warp (2 = gather ring)
-CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3, 2), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2, 2),
-           (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 3, 3, 1, 2))
+# hash space: 1 shared memory, 2 global 32-bit keys, 3 global 16-bit quotient entries, 0 auto
+CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2),
+           (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 3, 3, 1))
 
 
 def configure(ix, cfg, **kw):
     gather, warps, space, l2, pf = cfg[:5]
-    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf,
-                 stage_bufs=cfg[5] if len(cfg) > 5 else 0, **kw)
+    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf, **kw)
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)

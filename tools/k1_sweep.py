@@ -3,7 +3,7 @@ x beam width, CUDA-event timed with an L2 flush between repetitions.  Prints one
 gathered-row bandwidth (cmps x dim x 4 / time) and its fraction of the measured HBM peak.  A tuning aid, not the bench.
 
     python tools/k1_sweep.py --Ls 55 100 200 500 --configs w=2 w=4 w=2,hs=2 w=2,sb=2 ...
-config keys: w warps/query, hs hash_space, sb stage_bufs, sr stage_rows, c ctas/SM, hl hash_log2, l2 l2_hint, pf adj_prefetch
+config keys: w warps/query, hs hash_space, sr stage_rows, c ctas/SM, hl hash_log2, l2 l2_hint, pf adj_prefetch
 """
 import argparse
 import json
@@ -49,7 +49,7 @@ def main():
         kv = dict(x.split("=") for x in cfg.split(",") if x)
         g = lambda key, dflt=0: int(kv.get(key, dflt))
         ix.configure(gather=g("g"), warps_per_query=g("w"), ctas_per_sm=g("c"), stage_rows=g("sr"), hash_log2=g("hl"),
-                     hash_space=g("hs"), l2_hint=g("l2", 3), adj_prefetch=g("pf", 3), stage_bufs=g("sb"))
+                     hash_space=g("hs"), l2_hint=g("l2", 3), adj_prefetch=g("pf", 3))
         for L in a.Ls:
             for _ in range(2):
                 ix.search_device(q, k, L, ids, dists, cmps, hops, None, st)
