@@ -479,7 +479,10 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     double *sums = nullptr;
     unsigned long long *best = nullptr;
     // pair buffers serve P2 (two directions of every pruned list) and, per wave, the supply overflow of P4
-    const uint32_t wave = uint32_t(std::min<uint64_t>(131072, std::max<uint64_t>(1024, round_up(uint32_t(n / 32 + 1), 1024))));
+    // nodes per connectivity-enhancement wave: the searches of a wave see the supply graph as of the previous wave, so a
+    // wave is at most n/32 of the nodes; RG_BUILD_WAVE overrides (tools/build_quality_c1.py measures the sensitivity)
+    uint32_t wave = uint32_t(std::min<uint64_t>(131072, std::max<uint64_t>(1024, round_up(uint32_t(n / 32 + 1), 1024))));
+    if (const char *e = std::getenv("RG_BUILD_WAVE")) wave = uint32_t(std::max<long long>(256, std::min<long long>(1 << 20, atoll(e))));
     const uint64_t pair_cap = std::max<uint64_t>(n_train * 2ull * M, uint64_t(wave) * M);
     RG_CUDA_OK(sc.alloc(&S, n * uint64_t(stride)));
     RG_CUDA_OK(sc.alloc(&owner, n));

@@ -96,16 +96,33 @@ __device__ __forceinline__ uint32_t hash16_home(const SearchParams &p, uint32_t 
     *rem = x & ((1u << p.h16_rbits) - 1u);
     return x >> p.h16_rbits;
 }
-__device__ __forceinline__ uint32_t visited_test_and_set16(unsigned short *table, const SearchParams &p, uint32_t id) {
+// Two 16-bit entries share a 32-bit word and every update is ONE 32-bit atomicCAS on that word (CUDA's 16-bit atomicCAS
+// is a software loop - a load, then a 32-bit CAS - i.e. two dependent memory round trips per probe; ncu showed it as the
+// top stall of the kernel).  The first touch of a word bets that both halves are still empty: if the CAS succeeds the id
+// is inserted in one round trip, and if it fails the returned word tells whether the id is already there (also one round
+// trip) or which half is taken (then a second CAS, or the next slot, with the line already in L2).
+__device__ __forceinline__ uint32_t visited_test_and_set16(uint32_t *table32, const SearchParams &p, uint32_t id) {
     const uint32_t mask = (1u << p.hash_log2) - 1u;
     uint32_t rem;
     uint32_t slot = hash16_home(p, id, &rem);
     const uint32_t hi = rem << p.h16_dbits;
+    uint32_t cur = 0, cur_word = 0xFFFFFFFFu;  // last observed content of word `cur_word`
     for (uint32_t d = 0; d <= p.h16_maxd; ++d) {
-        const unsigned short want = (unsigned short)(hi | d);
-        const unsigned short old = atomicCAS(table + slot, (unsigned short)0xFFFFu, want);
-        if (old == 0xFFFFu) return 1u;
-        if (old == want) return 0u;     // same displacement -> same home slot, same remainder -> same id
+        const uint32_t want = hi | d, widx = slot >> 1, sh = (slot & 1u) << 4;
+        uint32_t *w = table32 + widx;
+        if (widx != cur_word) {
+            cur = atomicCAS(w, 0xFFFFFFFFu, ~(0xFFFFu << sh) | (want << sh));
+            if (cur == 0xFFFFFFFFu) return 1u;  // both halves were empty: inserted
+            cur_word = widx;
+        }
+        for (;;) {
+            const uint32_t e = (cur >> sh) & 0xFFFFu;
+            if (e == want) return 0u;           // same displacement -> same home slot, same remainder -> same id
+            if (e != 0xFFFFu) break;            // taken by another id: next slot
+            const uint32_t old = atomicCAS(w, cur, (cur & ~(0xFFFFu << sh)) | (want << sh));
+            if (old == cur) return 1u;
+            cur = old;                          // the word changed under us: look again
+        }
         slot = (slot + 1) & mask;
     }
     return 2u;
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     __syncthreads();
 
     auto visit = [&](uint32_t id) -> uint32_t {
-        if (kHash == kHashGlobal16) return visited_test_and_set16(hash16, p, id);
+        if (kHash == kHashGlobal16) return visited_test_and_set16(hash32, p, id);
         return visited_test_and_set32(hash32, p.hash_log2, id);
     };
 
