@@ -113,7 +113,7 @@ def prepare(args, rank, world, device):
     n_train = args.train or max(50_000, args.n // 5)
     base, train, test = synth.make_torch(args.n, n_train, args.queries * world, args.dim, seed=args.seed, device=device,
                                          normalize=args.normalize)
-    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}_gpu" + ("_unit" if args.normalize else "")
+    tag = f"n{args.n}_t{n_train}_d{args.dim}_s{args.seed}_M{args.M_sq}_{args.M_pjbp}_{args.L_pjpq}_gpu2" + ("_unit" if args.normalize else "")  # gpu2: builder with n/256-node waves
     os.makedirs(args.cache, exist_ok=True)
     index_path = os.path.join(args.cache, tag + ".index")
     info = {"n_train": n_train, "index_cached": os.path.exists(index_path), "builder": "rg_build_roargraph_device (GPU)"}

@@ -479,10 +479,13 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     double *sums = nullptr;
     unsigned long long *best = nullptr;
     // pair buffers serve P2 (two directions of every pruned list) and, per wave, the supply overflow of P4
-    // nodes per connectivity-enhancement wave: the searches of a wave see the supply graph as of the previous wave, so a
-    // wave is at most n/32 of the nodes; RG_BUILD_WAVE overrides (tools/build_quality_c1.py measures the sensitivity)
-    uint32_t wave = uint32_t(std::min<uint64_t>(131072, std::max<uint64_t>(1024, round_up(uint32_t(n / 32 + 1), 1024))));
-    if (const char *e = std::getenv("RG_BUILD_WAVE")) wave = uint32_t(std::max<long long>(256, std::min<long long>(1 << 20, atoll(e))));
+    // Nodes per connectivity-enhancement wave.  The searches of a wave see the supply graph as of the previous wave, while in
+    // the reference a node sees the lists and reverse edges of (nearly) every node processed before it (:1192-1220), and
+    // that staleness costs graph quality: on C1 (100K nodes) waves of 16 % / 4 % / 1 % / 0.5 % of the nodes end 0.050 /
+    // 0.007 / 0.0016 / 0.001 below the reference's recall@10 curve, the last one inside the spread of two reference builds
+    // (profiles/r02_build_quality_c1_waves.txt).  So a wave is n/256 of the nodes (>= 128, <= 131072); RG_BUILD_WAVE overrides.
+    uint32_t wave = uint32_t(std::min<uint64_t>(131072, std::max<uint64_t>(128, round_up(uint32_t(n / 256 + 1), 128))));
+    if (const char *e = std::getenv("RG_BUILD_WAVE")) wave = uint32_t(std::max<long long>(32, std::min<long long>(1 << 20, atoll(e))));
     const uint64_t pair_cap = std::max<uint64_t>(n_train * 2ull * M, uint64_t(wave) * M);
     RG_CUDA_OK(sc.alloc(&S, n * uint64_t(stride)));
     RG_CUDA_OK(sc.alloc(&owner, n));

@@ -419,7 +419,8 @@ std::vector<Neighbor> score_unique(const BuildCtx &c, uint32_t owner, const std:
 // PruneProjectionReverseCandidates, :1527-1610 (with_fill = true, no phantoms) and
 // PruneProjectionInternalReverseCandidates, :1434-1525 (with_fill = false, phantoms)
 void prune_reverse(const BuildCtx &c, uint32_t owner, std::vector<uint32_t> &list, bool internal) {
-    std::vector<Neighbor> q = score_unique(c, owner, list, internal ? list.size() : 0);
+    static const bool no_phantoms = std::getenv("RG_HOST_NO_PHANTOMS") != nullptr;  // experiment switch (graph construction)
+    std::vector<Neighbor> q = score_unique(c, owner, list, internal && !no_phantoms ? list.size() : 0);
     std::sort(q.begin(), q.end());
     std::vector<uint32_t> kept;
     kept.reserve(c.M * 2);

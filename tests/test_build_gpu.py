@@ -28,7 +28,7 @@ def test_gpu_build_matches_cpu_build_quality(capi, metric, n, dim, M_sq, M, L_bu
     import torch
     from mysteryann_b200 import hostlib, io, synth
 
-    base, train, test = synth.make_numpy(n, n, 500, dim, seed=n + dim, normalize=(dim == 512))
+    base, train, test = synth.make_numpy(n, n, 2000, dim, seed=n + dim, normalize=(dim == 512))
     knn, _ = capi.knn_exact(base, train, M_sq, metric=metric)
     gt, _ = capi.knn_exact(base, test, 10, metric=metric)
 
@@ -65,12 +65,15 @@ def test_gpu_build_matches_cpu_build_quality(capi, metric, n, dim, M_sq, M, L_bu
               f"cmps {a['cmps'].mean():.0f}/{b['cmps'].mean():.0f}")
         gaps.append((L, ra, rb))
     print("degrees gpu/cpu", deg.mean(), cdeg.mean(), deg.max(), cdeg.max(), "phases", g.phase_seconds)
-    # Both builds are order-dependent (threads on the CPU, waves + atomics on the GPU), and with 500 test queries one
-    # recall value carries ~0.01 of sampling noise; at the smallest beam widths a slightly sparser graph (fewer cmps per
-    # query, printed above) moves recall the most, so the margin is wider there.
+    # Both builds are order-dependent (threads on the CPU, waves of n/256 nodes + atomics on the GPU).  Measured at C1
+    # against two 16-thread builds of the compiled reference (profiles/r02_build_quality_c1*.txt): the GPU build ends
+    # <= 0.002 below the reference curve at every L_pq of the sweep, the two reference builds differ by up to 0.0018.
+    # Here: 2000 test queries (~0.003 sampling noise on a recall DIFFERENCE of two graphs over the same queries), graphs
+    # of 6-20K nodes where a wave is 0.6-2 % of the nodes; the small L2 graph (M_pjbp = 14, L_pjpq = 60) sits 0.002-0.009
+    # below its CPU build (mean -0.005), the other two within +-0.001 on average.
     for L, ra, rb in gaps:
-        assert ra >= rb - (0.06 if L <= 20 else 0.025), gaps
-    assert np.mean([ra - rb for _, ra, rb in gaps]) > -0.02, gaps
+        assert ra >= rb - (0.012 if L <= 20 else 0.006), gaps
+    assert np.mean([ra - rb for _, ra, rb in gaps]) > -0.006, gaps
     for x in (ix_gpu, ix_cpu, ix_dl):
         x.close()
     g.close()
