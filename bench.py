@@ -139,7 +139,8 @@ def prepare(args, rank, world, device):
         dist.barrier()
         info["knn_s"] = round(time.time() - t0, 2)
         info["knn_tflops"] = round(2.0 * args.n * n_train * args.dim / (time.time() - t0) / 1e12, 1)
-        info["knn_parallelism"] = f"base sharded over {world} GPUs, NCCL all-to-all + K4 merge"
+        info["knn_parallelism"] = (f"base sharded over {world} GPUs, rg_knn_exact_sharded + all-gather of the merged lists; first call "
+                                   "(includes NCCL communicator set-up and scratch allocation; wall clock) - roofline_knn is the timed figure")
         if rank != 0:
             knn_ids = None
     if rank == 0 and need_build:

@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -208,11 +209,42 @@ rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shard, uint
     const std::vector<uint64_t> qb = rg::split_bounds(nq, world);
     const uint64_t mine = qb[size_t(rank) + 1] - qb[size_t(rank)];
     const uint64_t longest = qb[1] - qb[0];
-    // segment rows per rank and chunk: large enough for full K2 query batches, small enough that the four exchange
-    // buffers (world * seg * K entries each) stay around a gigabyte in total
-    uint64_t seg = std::max<uint64_t>(131072, (uint64_t(1) << 27) / (uint64_t(world) * K));
-    seg = std::min<uint64_t>(seg, std::max<uint64_t>(longest, 1));
+    // segment rows per rank and chunk: whole K2 query batches (131072), as many as keep the four exchange buffers
+    // (world * seg * K entries each) around a gigabyte in total
+    const uint64_t kBatch = 131072;
+    uint64_t seg = std::max<uint64_t>(kBatch, ((uint64_t(1) << 27) / (uint64_t(world) * K)) / kBatch * kBatch);
+    if (const char *e = getenv("RG_KNN_SHARD_SEG")) seg = uint64_t(std::max<long long>(1, atoll(e)));  // tests: force the chunked path
     static thread_local rg::ShardedScratch scratch;
+
+    if (longest <= seg) {
+        // Everything fits one chunk: ONE K2/K3 call over all queries (full 131072-query batches instead of `world` small
+        // segments), the part lists laid out like the query array so that slice p starts at row qb[p].
+        if ((s = scratch.ensure(std::max<uint64_t>(nq, uint64_t(world) * longest) * K)) != RG_OK) return s;
+        s = rg::knn::knn_device(d_base_shard, n_shard, id_base, d_queries, nq, dim, metric, K, scratch.part_ids, scratch.part_d, st,
+                                stats, false);
+        if (s != RG_OK) return s;
+        RG_NCCL_OK(api.GroupStart());
+        for (int p = 0; p < world; ++p) {
+            const uint64_t rows_p = qb[size_t(p) + 1] - qb[size_t(p)];
+            if (rows_p) {
+                RG_NCCL_OK(api.Send(scratch.part_ids + qb[size_t(p)] * K, rows_p * K, ncclUint32, p, comm, st));
+                RG_NCCL_OK(api.Send(scratch.part_d + qb[size_t(p)] * K, rows_p * K, ncclFloat32, p, comm, st));
+            }
+            if (mine) {
+                RG_NCCL_OK(api.Recv(scratch.recv_ids + uint64_t(p) * mine * K, mine * K, ncclUint32, p, comm, st));
+                RG_NCCL_OK(api.Recv(scratch.recv_d + uint64_t(p) * mine * K, mine * K, ncclFloat32, p, comm, st));
+            }
+        }
+        RG_NCCL_OK(api.GroupEnd());
+        if (mine) {
+            s = rg_knn_merge_device(scratch.recv_ids, scratch.recv_d, uint32_t(world), mine, K, metric, d_ids, d_dists, device, st);
+            if (s != RG_OK) return s;
+            stats[0] += 1;
+        }
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        rg::knn::set_last_stats(stats);
+        return RG_OK;
+    }
     if ((s = scratch.ensure(uint64_t(world) * seg * K)) != RG_OK) return s;
 
     bool first = true;
@@ -252,7 +284,6 @@ rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shard, uint
             total[0] += 1;
         }
     }
-    (void)mine;
     RG_CUDA_OK(cudaStreamSynchronize(st));
     rg::knn::set_last_stats(total);
     return RG_OK;

@@ -167,10 +167,12 @@ def test_knn_sharded_capi_world1(capi, oracle):
         capi.knn_exact_sharded(db, 0, dq, K, ids, d, None, 0, 2, metric=1)
 
 
-def test_knn_sharded_capi_two_gpus(capi, oracle):
+@pytest.mark.parametrize("seg", (0, 256))
+def test_knn_sharded_capi_two_gpus(capi, oracle, seg, monkeypatch):
     """Two base shards on two GPUs, one host thread per GPU (the layout of compute_groundtruth --devices 2): communicators
-    from rg_nccl_comm_init_all, grouped ncclSend/ncclRecv exchange and K4 merge inside rg_knn_exact_sharded.  Skipped on a
-    one-GPU box."""
+    from rg_nccl_comm_init_all, grouped ncclSend/ncclRecv exchange and K4 merge inside rg_knn_exact_sharded - once as a single
+    chunk (one K2 call over all queries), once with 256-row segments (the chunked path of C4-size query sets).  Skipped on
+    a one-GPU box."""
     import ctypes as C
     import threading
 
@@ -179,6 +181,8 @@ def test_knn_sharded_capi_two_gpus(capi, oracle):
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    if seg:
+        monkeypatch.setenv("RG_KNN_SHARD_SEG", str(seg))
     assert capi.lib().rg_nccl_version() > 0
     n, nq, dim, K = 30000, 1001, 200, 30
     base, q, _ = synth.make_numpy(n, nq, 1, dim, seed=12)
