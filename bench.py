@@ -159,16 +159,21 @@ def prepare(args, rank, world, device):
         info["graph_build_s"] = round(time.time() - t0, 2)
         info["graph_build_phases_s"] = {k: round(v, 2) for k, v in g.phase_seconds.items()}
         del knn_ids
-        ep, offsets, adj = g.download()
-        io.write_index(index_path + ".tmp", ep, offsets, adj)
-        np.savez(index_path + ".csr.tmp.npz", ep=np.uint32(ep), offsets=offsets, adj=adj)  # fast reload for the other ranks
-        os.replace(index_path + ".csr.tmp.npz", index_path + ".csr.npz")
-        os.replace(index_path + ".tmp", index_path)
+        if args.n <= 50_000_000:  # the 100M-row index (13 GB of files) is used in place, single GPU, no CPU arm
+            ep, offsets, adj = g.download()
+            io.write_index(index_path + ".tmp", ep, offsets, adj)
+            np.savez(index_path + ".csr.tmp.npz", ep=np.uint32(ep), offsets=offsets, adj=adj)  # fast reload for the other ranks
+            os.replace(index_path + ".csr.tmp.npz", index_path + ".csr.npz")
+            os.replace(index_path + ".tmp", index_path)
+        else:
+            ep, offsets, adj = g.ep, None, None
+            info["index_file"] = "not written (used in place)"
         index = capi.Index.from_graph(base, g, metric=capi.METRIC_IP)
         info.update(avg_degree=round(g.nnz / args.n, 2), max_degree=int(g.max_degree), ep=int(ep))
         g.close()
         del offsets, adj
-        json.dump(info, open(index_path + ".info.json", "w"))  # build timings travel with the cached index
+        if args.n <= 50_000_000:
+            json.dump(info, open(index_path + ".info.json", "w"))  # build timings travel with the cached index
     elif rank == 0 and os.path.exists(index_path + ".info.json"):
         cached = json.load(open(index_path + ".info.json"))
         cached.update(index_cached=True)
