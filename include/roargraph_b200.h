@@ -88,8 +88,10 @@ RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries,
  * mbarrier); warps_per_query: warps of the CTA that owns a query (1..8); stage_rows: rows per warp staging buffer. */
 RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
                                      int hash_log2);
-/* Named options: "hash_space" = 0 auto, 1 visited hash in shared memory, 2 in global memory with 32-bit keys (L2-resident
- * slab per CTA), 3 in global memory with 16-bit quotient entries where the id range allows (what auto picks);
+/* Named options: "hash_space" = visited set of a query: 0 auto (= 4), 1 hash table in shared memory, 2 / 3 a slab per CTA in
+ * global memory probed with atomicCAS (32-bit keys / 16-bit quotient entries where the id range allows), 4 a slab of
+ * buckets per CTA in global memory without atomics (each warp owns a bucket range; 16-bit quotient entries where the id
+ * range allows, else 32-bit ids), 5 the same with 32-bit ids always;
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
  * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its

@@ -243,8 +243,8 @@ rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_query, int
 rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
     if (!ix || !name) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_set_option: null argument");
     if (!strcmp(name, "hash_space")) {
-        if (value < 0 || value > 3)
-            return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory), 2 (global memory, 32-bit keys) or 3 (global memory, 16-bit quotient entries when the id range allows)");
+        if (value < 0 || value > 5)
+            return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_space must be 0 (auto), 1 (shared memory), 2 / 3 (global memory, atomicCAS on 32-bit keys / 16-bit quotient entries), 4 (global memory, buckets without atomics; 16-bit entries when the id range allows) or 5 (buckets of 32-bit ids)");
         ix->cfg_hash_space = value;
         return RG_OK;
     }

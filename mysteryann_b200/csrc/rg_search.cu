@@ -42,7 +42,17 @@ constexpr int kMaxWarps = 8;
 // shared control words
 enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */ };
 // visited-set flavours
-enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2 };
+enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2, kHashBucket16 = 3, kHashBucket32 = 4 };
+// kHashBucket*: no atomics.  The slab is an array of buckets (16 B = 8 x 16-bit quotient entries, or 32 B = 8 x 32-bit
+// ids), filled front to back.  Warp w of the CTA owns the contiguous bucket range whose home buckets satisfy
+// floor(home * W / buckets) == w and is the only one that ever reads or writes it, so a lookup is ONE vector load of the
+// home bucket (ld.global.cg), the decision is taken in registers, simultaneous inserts of one hop are arbitrated inside
+// the warp (match.any on the bucket index, rank = slot), and the insert is a plain store nobody waits for.  Because a
+// load has no side effect it can be issued a hop AHEAD for the node the search will most likely expand next: when that
+// speculation holds (80 % of the hops at L_pq = 500) the visited filter costs no memory round trip at all.
+#ifndef RG_K1_SPEC_SECTOR_REGS
+#define RG_K1_SPEC_SECTOR_REGS 1  // 16-bit buckets: keep the speculated node's bucket contents in registers (0: L2 prefetch only)
+#endif
 
 struct SearchParams {
     const float *base;
@@ -61,6 +71,7 @@ struct SearchParams {
     // 16-bit quotient entries (kHashGlobal16): x = (id * h16_mult) mod 2^h16_bits is a bijection of the id range; the home
     // slot is its top hash_log2 bits, the entry stores the remaining h16_rbits bits and the probe displacement
     uint32_t h16_bits, h16_rbits, h16_dbits, h16_maxd, h16_mult;
+    uint32_t bkt_log2;         // kHashBucket*: log2(number of buckets); h16_* then describe the bucket-level quotient
     uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
@@ -76,7 +87,7 @@ struct SearchParams {
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
     uint32_t off_pool, off_cand, off_sorted, off_pos, off_ctrl, off_hash, off_warp;
-    uint32_t warp_bytes, woff_cid, woff_stage;  // per-warp area: [mbarrier][candidate ids][row staging]
+    uint32_t warp_bytes, woff_cid, woff_mine, woff_stage;  // per-warp area: [mbarrier][candidate ids][ids to filter][row staging]
 };
 
 // ---- exact visited set --------------------------------------------------------------------------
@@ -129,6 +140,104 @@ __device__ __forceinline__ uint32_t visited_test_and_set16(uint32_t *table32, co
 }
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr)); }
 
+// ---- bucketed visited set without atomics (kHashBucket16 / kHashBucket32) ------------------------------
+__device__ __forceinline__ uint4 ld_cg_v4(const void *ptr) {  // L2-only vector load: never served from a stale L1 line
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+// home bucket of an id and the part of the entry that does not depend on the displacement
+template <int kHash>
+__device__ __forceinline__ uint32_t bucket_home(const SearchParams &p, uint32_t id, uint32_t *tag) {
+    if (kHash == kHashBucket16) {
+        const uint32_t x = (id * p.h16_mult) & ((1u << p.h16_bits) - 1u);
+        *tag = (x & ((1u << p.h16_rbits) - 1u)) << p.h16_dbits;
+        return x >> p.h16_rbits;
+    }
+    *tag = id;
+    return (id * 0x9E3779B1u) >> (32 - p.bkt_log2);
+}
+__device__ __forceinline__ void bucket_scan16(const uint4 s, uint32_t want, bool *found, uint32_t *cnt) {
+    const uint32_t w[4] = {s.x, s.y, s.z, s.w};
+    bool f = false;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
+        f |= (lo == want) | (hi == want);
+        c += (lo != 0xFFFFu ? 1u : 0u) + (hi != 0xFFFFu ? 1u : 0u);
+    }
+    *found = f;
+    *cnt = c;
+}
+__device__ __forceinline__ void bucket_scan32(const uint4 a, const uint4 b, uint32_t want, bool *found, uint32_t *cnt) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    bool f = false;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f |= w[i] == want;
+        c += w[i] != kEmpty ? 1u : 0u;
+    }
+    *found = f;
+    *cnt = c;
+}
+// Warp-collective test-and-set of one id per active lane inside this warp's bucket range [blo, bhi).  Returns 1 = first
+// visit, 0 = already visited (or inactive lane), 2 = displacement field exhausted.  `pre` is the content of the lane's home
+// bucket when have_pre (loaded a hop ahead; nothing has been inserted since).  Every round: load the current bucket, look
+// for the entry, count the used slots; lanes that want to append to the same bucket take consecutive slots in lane order
+// (match.any); whoever finds the bucket full moves to the next one (displacement + 1) and sees this round's stores there
+// because __syncwarp orders them before the next round's loads.
+template <int kHash>
+__device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, const SearchParams &p, uint32_t blo, uint32_t bhi,
+                                                        bool active, uint32_t id, bool have_pre, const uint4 pre, uint32_t lane) {
+    uint32_t tag;
+    uint32_t bucket = bucket_home<kHash>(p, id, &tag), d = 0, res = 0;
+    const uint32_t dummy = 0x80000000u | lane;  // ids are < 2^31
+    const uint32_t peers = __match_any_sync(0xffffffffu, active ? id : dummy);
+    bool pending = active && (uint32_t(__ffs(peers)) - 1u == lane);  // a duplicate inside the round: its first lane decides
+    bool need_load = !have_pre;
+    uint4 s0 = pre, s1 = make_uint4(0, 0, 0, 0);
+    while (__any_sync(0xffffffffu, pending)) {
+        bool found = false;
+        uint32_t cnt = 0;
+        const uint32_t want = kHash == kHashBucket16 ? (tag | d) : id;
+        if (kHash == kHashBucket16) {
+            if (pending && need_load) s0 = ld_cg_v4(slab + (size_t(bucket) << 4));
+            bucket_scan16(s0, want, &found, &cnt);
+        } else {
+            if (pending) {
+                s0 = ld_cg_v4(slab + (size_t(bucket) << 5));
+                s1 = ld_cg_v4(slab + (size_t(bucket) << 5) + 16);
+            }
+            bucket_scan32(s0, s1, want, &found, &cnt);
+        }
+        if (found) pending = false;
+        const bool prop = pending && cnt < 8u;
+        const uint32_t grp = __match_any_sync(0xffffffffu, prop ? bucket : dummy);
+        if (prop) {
+            const uint32_t slot = cnt + __popc(grp & lanemask_lt());
+            if (slot < 8u) {
+                if (kHash == kHashBucket16) __stcg(reinterpret_cast<unsigned short *>(slab) + (size_t(bucket) << 3) + slot, (unsigned short)want);
+                else __stcg(reinterpret_cast<uint32_t *>(slab) + (size_t(bucket) << 3) + slot, want);
+                res = 1u;
+                pending = false;
+            }
+        }
+        if (pending) {  // bucket full
+            if (++d > p.h16_maxd) {
+                res = 2u;
+                pending = false;
+            } else {
+                bucket = (bucket + 1u == bhi) ? blo : bucket + 1u;
+                need_load = true;
+            }
+        }
+        __syncwarp();
+    }
+    return res;
+}
+
 // first index in sorted keys[0..n) whose key (flag bit cleared) is >= key
 __device__ __forceinline__ uint32_t lower_bound_key(const uint64_t *keys, uint32_t n, uint64_t key) {
     uint32_t lo = 0, hi = n;
@@ -158,9 +267,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     uint64_t *s_mbar = reinterpret_cast<uint64_t *>(wa);
     uint32_t *s_cid = reinterpret_cast<uint32_t *>(wa + p.woff_cid);
     float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
+    constexpr bool kBucket = kHash == kHashBucket16 || kHash == kHashBucket32;
+    uint32_t *s_mine = reinterpret_cast<uint32_t *>(wa + p.woff_mine);  // bucket flavours: ids of the expanded row this warp owns
     uint32_t *hash32 = kHash == kHashShared ? reinterpret_cast<uint32_t *>(smem_raw + p.off_hash)
+                       : kBucket            ? p.ghash + (size_t(blockIdx.x) << (p.bkt_log2 + (kHash == kHashBucket16 ? 2 : 3)))
                                             : p.ghash + (size_t(blockIdx.x) << (kHash == kHashGlobal16 ? p.hash_log2 - 1 : p.hash_log2));
     unsigned short *hash16 = reinterpret_cast<unsigned short *>(hash32);
+    unsigned char *slab = reinterpret_cast<unsigned char *>(hash32);
+    // bucket flavours: this warp's bucket range (home buckets with floor(home * W / buckets) == warp)
+    const uint32_t blo = kBucket ? uint32_t(((uint64_t(warp) << p.bkt_log2) + W - 1) / W) : 0u;
+    const uint32_t bhi = kBucket ? uint32_t(((uint64_t(warp + 1) << p.bkt_log2) + W - 1) / W) : 0u;
 
     const uint32_t dim = p.dim, n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
@@ -185,10 +301,58 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         return visited_test_and_set32(hash32, p.hash_log2, id);
     };
 
+    // speculation: adjacency words of the node expected to be expanded next (see step 2 above) and, bucket flavours, the
+    // number of its neighbours this warp owns (listed in s_mine) with the content of lane l's home bucket
+    uint32_t spec_id = kEmpty, spec_deg = 0, sreg[3] = {kEmpty, kEmpty, kEmpty};
+    uint32_t spec_n = 0, self = 0;
+    uint4 spec_sec = make_uint4(0, 0, 0, 0);
+
+    // bucket flavours: the ids of an adjacency row (first 96 words in wr, word i = wr[i / 32] of lane i % 32) whose home
+    // bucket belongs to this warp, compacted into s_mine in row order
+    auto compact_mine = [&](const uint32_t *row, uint32_t deg, const uint32_t (&wr)[3]) -> uint32_t {
+        uint32_t n = 0;
+        for (uint32_t it = 0; it * 32 < deg; ++it) {
+            const uint32_t idx = lane + 32 * it;
+            uint32_t word;
+            if (it == 0) word = wr[0];
+            else if (it == 1) word = wr[1];
+            else if (it == 2) word = wr[2];
+            else word = (idx < deg) ? __ldg(row + 1 + idx) : kEmpty;
+            bool mine = idx < deg && !(kBuild && word == self);
+            uint32_t tag;
+            if (mine) mine = ((bucket_home<kHash>(p, word, &tag) * W) >> p.bkt_log2) == warp;
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            if (mine) s_mine[n + __popc(m & lanemask_lt())] = word;
+            n += __popc(m);
+        }
+        __syncwarp();
+        return n;
+    };
+    // bucket flavours, while the hop's first rows are in flight: list the speculated node's neighbours this warp owns and
+    // request their home buckets (into registers, or into L2)
+    auto spec_block = [&]() {
+        if (!kBucket || spec_id == kEmpty) return;
+        if (spec_deg > 96u) {  // longer rows are not speculated on
+            spec_id = kEmpty;
+            return;
+        }
+        spec_n = compact_mine(nullptr, spec_deg, sreg);
+        for (uint32_t i = lane; i < spec_n; i += 32) {
+            uint32_t tag;
+            const uint32_t b = bucket_home<kHash>(p, s_mine[i], &tag);
+            if (kHash == kHashBucket16) {
+                if (RG_K1_SPEC_SECTOR_REGS && i < 32) spec_sec = ld_cg_v4(slab + (size_t(b) << 4));
+                else prefetch_l2(slab + (size_t(b) << 4));
+            } else {
+                prefetch_l2(slab + (size_t(b) << 5));
+            }
+        }
+    };
+
     // Gathers and scores this warp's candidates s_cid[0..n); keys below `tail` are appended to the CTA-wide list.
     // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
     // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
-    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key) {
+    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key, bool do_spec) {
         for (uint32_t c0 = 0; c0 < n; c0 += BR) {
             const uint32_t rows = min(BR, n - c0);
             const float *stage = s_stage;
@@ -202,6 +366,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     for (uint32_t r = lane; r < rows; r += 32)
                         bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
                 }
+                if (do_spec && c0 == 0) spec_block();
                 mbar_wait(s_mbar, mb_phase);
                 mb_phase ^= 1u;
             } else {
@@ -212,6 +377,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     cp_async16(s_stage + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
                 }
                 cp_async_commit();
+                if (do_spec && c0 == 0) spec_block();
                 cp_async_wait<0>();
                 __syncwarp();
             }
@@ -268,7 +434,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             for (uint32_t i = tid; i < cpr; i += T) dst[i] = src[i];
             uint4 *h4 = reinterpret_cast<uint4 *>(hash32);
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            const uint32_t n_vec = 1u << (p.hash_log2 - (kHash == kHashGlobal16 ? 3 : 2));
+            const uint32_t n_vec = kBucket ? 1u << (p.bkt_log2 + (kHash == kHashBucket16 ? 0 : 1))
+                                           : 1u << (p.hash_log2 - (kHash == kHashGlobal16 ? 3 : 2));
             for (uint32_t i = tid; i < n_vec; i += T) h4[i] = e4;
         }
         __syncthreads();
@@ -276,19 +443,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         uint32_t size = 0, cur = 0, hops = 0, nvis = 0, hp = 0;  // hp: parity of the hop's control words
         uint64_t tail = ~0ull;  // (distance,id) of the last entry once the pool is full, else +inf
         bool have_cur = false, overflow = false;
-        // speculation: adjacency words of the node expected to be expanded next (see step 2 above)
-        uint32_t spec_id = kEmpty, spec_deg = 0, sreg[3] = {kEmpty, kEmpty, kEmpty};
+        spec_id = kEmpty;
 
         // entry point: scored and inserted, NOT marked visited (src/index_bipartite.cpp:2337-2353); the build-time
         // search does mark it (:1309)
-        const uint32_t self = p.node_lo + qi;
+        self = p.node_lo + qi;
+        if (kBuild && kBucket) {  // every warp takes part; the owner of the entry point's home bucket inserts it
+            uint32_t tag;
+            const bool act = lane == 0 && ((bucket_home<kHash>(p, p.ep, &tag) * W) >> p.bkt_log2) == warp;
+            bucket_test_and_set<kHash>(slab, p, blo, bhi, act, p.ep, false, spec_sec, lane);
+        }
         if (warp == 0) {
             if (lane == 0) {
                 s_cid[0] = p.ep;
-                if (kBuild) visit(p.ep);
+                if (kBuild && !kBucket) visit(p.ep);
             }
             __syncwarp();
-            gather_and_score(1, tail, kCtlHop0, ~0ull);
+            gather_and_score(1, tail, kCtlHop0, ~0ull, false);
         }
 
         for (;;) {
@@ -296,7 +467,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             const uint32_t ctl = kCtlHop0 + 4 * hp, octl = kCtlHop0 + 4 * (hp ^ 1u);  // this hop's / the other hop's words
             const uint32_t C = s_ctrl[ctl + 0];
             nvis = s_ctrl[kCtlNvis];
-            if (kHash == kHashGlobal16 && s_ctrl[kCtlHashFull]) {  // a displacement field ran out: big-table pass
+            if ((kHash == kHashGlobal16 || kBucket) && s_ctrl[kCtlHashFull]) {  // a displacement field ran out: big-table pass
                 overflow = true;
                 break;
             }
@@ -405,19 +576,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 overflow = true;
                 break;
             }
-            // adjacency row: neighbour j is handled by warp j % W, lane (j / W) % 32; the first three rounds are
-            // requested together with the degree word: one DRAM round trip - or none at all when this node was the
-            // one read ahead during the previous hop
+            // adjacency row.  CAS flavours: neighbour j is handled by warp j % W, lane (j / W) % 32; bucket flavours: every
+            // warp reads the whole row (word i by lane i % 32) and keeps the neighbours whose home bucket it owns.  The first
+            // three rounds are requested together with the degree word: one DRAM round trip - or none at all when this
+            // node was the one read ahead during the previous hop
             const uint32_t *row = p.adj + size_t(cur_id) * p.adj_stride;
+            const bool spec_hit = spec_id == cur_id;
             uint32_t wreg[3], deg;
-            if (spec_id == cur_id) {
+            if (spec_hit) {
 #pragma unroll
                 for (uint32_t it = 0; it < 3; ++it) wreg[it] = sreg[it];
                 deg = spec_deg;
             } else {
 #pragma unroll
                 for (uint32_t it = 0; it < 3; ++it) {
-                    const uint32_t j = (lane + 32 * it) * W + warp;
+                    const uint32_t j = kBucket ? lane + 32 * it : (lane + 32 * it) * W + warp;
                     wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
                 }
                 deg = __ldg(row);
@@ -445,7 +618,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                         const uint32_t *nrow = p.adj + size_t(spec_id) * p.adj_stride;
 #pragma unroll
                         for (uint32_t it = 0; it < 3; ++it) {
-                            const uint32_t j = (lane + 32 * it) * W + warp;
+                            const uint32_t j = kBucket ? lane + 32 * it : (lane + 32 * it) * W + warp;
                             sreg[it] = (j + 1 < p.adj_stride) ? __ldg(nrow + 1 + j) : kEmpty;
                         }
                         spec_deg = __ldg(nrow);
@@ -453,26 +626,45 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 }
             }
             uint32_t n_w = 0;
-            for (uint32_t it = 0; it * 32 * W < deg; ++it) {
-                const uint32_t j = (lane + 32 * it) * W + warp;
-                uint32_t word;
-                if (it == 0) word = wreg[0];
-                else if (it == 1) word = wreg[1];
-                else if (it == 2) word = wreg[2];
-                else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
-                uint32_t v = 0;
-                if (j < deg && !(kBuild && word == self)) v = visit(word);
-                if (kHash == kHashGlobal16 && v == 2u) {
-                    s_ctrl[kCtlHashFull] = 1;
-                    v = 0;
+            if (kBucket) {
+                // this warp's neighbours are in s_mine: listed a hop ahead (speculation held) or now
+                const uint32_t n_mine = spec_hit ? spec_n : compact_mine(row, deg, wreg);
+                for (uint32_t r0 = 0; r0 < n_mine; r0 += 32) {
+                    const bool act = r0 + lane < n_mine;
+                    const uint32_t id = act ? s_mine[r0 + lane] : 0u;
+                    const bool pre = RG_K1_SPEC_SECTOR_REGS && kHash == kHashBucket16 && spec_hit && r0 == 0;
+                    uint32_t v = bucket_test_and_set<kHash>(slab, p, blo, bhi, act, id, pre, spec_sec, lane);
+                    if (v == 2u) {
+                        s_ctrl[kCtlHashFull] = 1;
+                        v = 0;
+                    }
+                    const bool fresh = v == 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                    if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = id;
+                    n_w += __popc(m);
                 }
-                const bool fresh = v == 1u;
-                const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
-                n_w += __popc(m);
+            } else {
+                for (uint32_t it = 0; it * 32 * W < deg; ++it) {
+                    const uint32_t j = (lane + 32 * it) * W + warp;
+                    uint32_t word;
+                    if (it == 0) word = wreg[0];
+                    else if (it == 1) word = wreg[1];
+                    else if (it == 2) word = wreg[2];
+                    else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
+                    uint32_t v = 0;
+                    if (j < deg && !(kBuild && word == self)) v = visit(word);
+                    if (kHash == kHashGlobal16 && v == 2u) {
+                        s_ctrl[kCtlHashFull] = 1;
+                        v = 0;
+                    }
+                    const bool fresh = v == 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                    if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
+                    n_w += __popc(m);
+                }
             }
             __syncwarp();
-            if (pf_next && spec_id != kEmpty && kHash != kHashShared) {
+            if (!kBucket && pf_next && spec_id != kEmpty && kHash != kHashShared) {
                 // pull the visited-hash slots the speculated node's neighbours map to into L2: one hop from now their
                 // atomicCAS probes are L2 hits instead of HBM round trips on the query's dependent chain
 #pragma unroll
@@ -492,7 +684,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
                 // a re-scored entry point lands here too; the merge drops it as a duplicate (neighbor.h:161) or the tail
                 // test drops it (neighbor.h:151), exactly like the reference
-                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp, next_key);
+                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp, next_key, true);
+            } else {
+                spec_block();
             }
         }
 
@@ -567,6 +761,8 @@ static SearchKernel pick_build(bool build) {
 }
 template <bool kIP, int kGather>
 static SearchKernel pick_hash(int hash_kind, bool build) {
+    if (hash_kind == kHashBucket16) return pick_build<kIP, 2, kHashBucket16>(build);  // bucket flavours: TMA gather only
+    if (hash_kind == kHashBucket32) return pick_build<kIP, 2, kHashBucket32>(build);
     if (hash_kind == kHashGlobal16) return pick_build<kIP, kGather, kHashGlobal16>(build);
     if (hash_kind == kHashGlobal32) return pick_build<kIP, kGather, kHashGlobal32>(build);
     return pick_build<kIP, kGather, kHashShared>(build);
@@ -579,8 +775,9 @@ static SearchKernel pick_kernel(bool ip, int gather, int hash_kind, bool build) 
 static bool persisting_window_fits(const rg_index *ix, uint64_t bytes);
 
 static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool fallback, bool build, Geometry *g,
-                               int warps_override = 0, bool allow16 = true) {
+                               int warps_override = 0, bool allow16 = true, int space_override = -1) {
     SearchParams &p = g->p;
+    const int space = space_override >= 0 ? space_override : ix->cfg_hash_space;
     memset(&p, 0, sizeof(p));
     p.dim = ix->dim;
     p.adj_stride = ix->adj_stride;
@@ -599,19 +796,43 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     if (warps_override) g->warps = warps_override;
     const uint32_t W = uint32_t(g->warps);
 
-    uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || ix->cfg_hash_space != 1);
+    uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || space != 1);
     p.fallback = fallback ? 1u : 0u;
     p.l2_hint = uint32_t(ix->cfg_l2_hint);
     p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
-    // visited set: a slab per CTA in global memory (L2-resident at the usual beam widths) unless shared memory was asked
-    // for (hash_space 1).  Entries are 16-bit quotients when the id range leaves >= 6 bits for the probe displacement
-    // at a table no larger (in bytes) than the 32-bit one (hash_space 3 asks for them, 2 for 32-bit keys).
-    const bool global_hash = fallback || build || hl > 15 || ix->cfg_hash_space != 1;
+    // visited set: a slab per CTA in global memory unless shared memory was asked for (hash_space 1).
+    //   hash_space 0 (auto) / 4: buckets without atomics - 16-bit quotient entries (8 per 16-byte bucket) when the id range
+    //                            leaves >= 3 displacement bits at no more than twice the slots, else 32-bit ids (8 per 32 B)
+    //   hash_space 5: 32-bit buckets;  2 / 3: round 1/2's atomicCAS tables (32-bit keys / 16-bit quotient entries)
+    const bool global_hash = fallback || build || hl > 15 || space != 1;
     if (fallback) hl = std::min<uint32_t>(22u, std::max<uint32_t>(16u, hl + 3));
     g->hash_kind = global_hash ? kHashGlobal32 : kHashShared;
-    if (global_hash && !fallback && ix->cfg_hash_space != 2 && allow16) {
-        uint32_t id_bits = 1;
-        while ((1ull << id_bits) < ix->n && id_bits < 32) ++id_bits;
+    uint32_t id_bits = 1;
+    while ((1ull << id_bits) < ix->n && id_bits < 31) ++id_bits;
+    const bool want_bucket = global_hash && !fallback && (space == 0 || space == 4 || space == 5);
+    p.hash_limit = 0;
+    if (want_bucket) {
+        hl = std::max<uint32_t>(hl, 6u);
+        const uint32_t hb = hl - 3;                                                      // 8 entries per bucket
+        const uint32_t hb16 = std::max<uint32_t>(hb, id_bits > 13 ? id_bits - 13 : 0);  // remainder <= 13 bits
+        if (space != 5 && allow16 && hb16 <= hb + 1 && hb16 <= 19) {
+            g->hash_kind = kHashBucket16;
+            p.bkt_log2 = hb16;
+            hl = hb16 + 3;
+            p.h16_bits = std::max(id_bits, hb16);
+            p.h16_rbits = p.h16_bits - hb16;
+            p.h16_dbits = std::min<uint32_t>(16u - p.h16_rbits, 8u);
+            p.h16_maxd = (1u << p.h16_dbits) - 2u;  // all-ones is kept for the empty entry
+            p.h16_mult = (uint32_t(double(1ull << p.h16_bits) * 0.6180339887498949) | 1u) & uint32_t((1ull << p.h16_bits) - 1);
+        } else {
+            g->hash_kind = kHashBucket32;
+            p.bkt_log2 = hb;
+            p.h16_maxd = 30;
+        }
+        // the smallest per-warp bucket range must stay longer than the longest probe walk
+        p.h16_maxd = std::min<uint32_t>(p.h16_maxd, std::max<uint32_t>(1u, ((1u << p.bkt_log2) / W) - 1u));
+        p.hash_limit = uint32_t((uint64_t(1) << hl) * 70 / 100);
+    } else if (global_hash && !fallback && space != 2 && allow16) {
         const uint32_t h16 = std::max<uint32_t>(hl, id_bits > 10 ? id_bits - 10 : 0);  // >= 6 displacement bits
         if (h16 <= hl + 1 && h16 <= 22) {
             g->hash_kind = kHashGlobal16;
@@ -625,8 +846,10 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
         }
     }
     p.hash_log2 = hl;
-    p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
-    g->slab_bytes = g->hash_kind == kHashShared ? 0 : (uint64_t(g->hash_kind == kHashGlobal16 ? 2 : 4) << hl);
+    if (!p.hash_limit) p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
+    g->slab_bytes = g->hash_kind == kHashShared ? 0
+                    : (uint64_t(g->hash_kind == kHashGlobal16 || g->hash_kind == kHashBucket16 ? 2 : 4) << hl);
+    const bool bucket = g->hash_kind == kHashBucket16 || g->hash_kind == kHashBucket32;
 
     uint32_t off = round_up(ix->dim * 4, 128);
     p.off_pool = off;
@@ -642,9 +865,11 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.off_hash = off;
     if (g->hash_kind == kHashShared) off += (4u << hl);
     p.off_warp = off;
-    const uint32_t cid_cap = round_up((ix->adj_stride - 1 + W - 1) / W, 8);
+    // CAS flavours: a warp filters every W-th neighbour; bucket flavours: any share of the row may hash into its range
+    const uint32_t cid_cap = bucket ? round_up(ix->adj_stride, 8) : round_up((ix->adj_stride - 1 + W - 1) / W, 8);
     p.woff_cid = 16;
-    p.woff_stage = round_up(16 + cid_cap * 4, 128);
+    p.woff_mine = p.woff_cid + cid_cap * 4;
+    p.woff_stage = round_up(p.woff_mine + (bucket ? cid_cap * 4 : 0), 128);
     p.warp_bytes = p.woff_stage + round_up(p.stage_rows * p.row_stride * 4, 128);
     off += W * p.warp_bytes;
     g->smem_bytes = off;
@@ -732,20 +957,19 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     Geometry g1, g2;
     rg_status s = make_geometry(ix, k, L, true, build, &g2);
     if (s != RG_OK) return s;
-    // Primary pass, automatic mode (same-box sweeps in profiles/r02_k1_sweep_*.txt): two warps per query; 32-bit hash keys
-    // while the slabs of all resident queries fit the persisting part of L2 (0.87 vs 0.84 of the HBM peak at L_pq = 55:
-    // the 16-bit CAS is a little slower while both hit L2), 16-bit quotient entries - half the slab - beyond that (0.75-0.79
-    // vs 0.71 at L_pq = 100, 0.64 vs 0.57 at 200, a tie at 500).  Four warps per query, which round 1 used to make 32-bit
-    // slabs fit at L_pq ~ 100, no longer pays: halving the resident queries costs more than the L2 hits return.
+    // Primary pass, automatic mode (same-box sweeps in profiles/r02_k1_sweep_*.txt): two warps per query; atomicCAS on 32-bit
+    // keys while the slabs of all resident queries fit the persisting part of L2 (L_pq <= ~75 at 10M rows: 0.89 of the HBM
+    // peak at L_pq = 55 against 0.85 for the buckets, whose warps each read the whole adjacency row); beyond that the
+    // bucketed visited set without atomics (0.67 vs 0.60 at L_pq = 200, 0.56 vs 0.51 at 500).
     const bool auto_hash = ix->cfg_hash_space == 0;
-    s = make_geometry(ix, k, L, false, build, &g1, 0, !auto_hash);
+    s = make_geometry(ix, k, L, false, build, &g1);
     if (s != RG_OK) return s;
-    if (auto_hash && g1.slab_bytes) {
-        const uint64_t cap = std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g1.ctas_per_sm);
-        if (!persisting_window_fits(ix, cap * g1.slab_bytes)) {
-            Geometry g;
-            if (make_geometry(ix, k, L, false, build, &g, 0, true) == RG_OK) g1 = g;
-        }
+    if (auto_hash && !build) {
+        Geometry g;
+        const rg_status s2 = make_geometry(ix, k, L, false, build, &g, 0, true, 2);
+        if (s2 == RG_OK && g.slab_bytes &&
+            persisting_window_fits(ix, std::min<uint64_t>(nq, uint64_t(ix->sm_count) * g.ctas_per_sm) * g.slab_bytes))
+            g1 = g;
     }
 
     // scratch: overflow list (one slot per query) and global hash slabs (one per CTA).  The fallback pass re-runs the few

@@ -41,9 +41,11 @@ def capi():
 
 # (gather, warps per query, visited-hash space, L2 hints, adjacency prefetch): cp.async / TMA bulk gathers, 1..8 warps per
 # query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch
-# hash space: 1 shared memory, 2 global 32-bit keys, 3 global 16-bit quotient entries, 0 auto
-CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 2, 1, 2),
-           (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 3, 3, 1))
+# hash space: 1 shared memory, 2 / 3 global atomicCAS tables (32-bit keys / 16-bit quotient entries), 4 / 5 global buckets
+# without atomics (16-bit entries where the id range allows / 32-bit ids), 0 auto (= 4)
+CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 5, 1, 2),
+           (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 4, 3, 1), (2, 1, 4, 3, 3), (2, 2, 5, 3, 3), (2, 4, 4, 0, 0),
+           (2, 8, 0, 3, 3))
 
 
 def configure(ix, cfg, **kw):
@@ -89,7 +91,7 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     if off[ep + 1] == off[ep]:
         ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    for cfg in CONFIGS[:5] + CONFIGS[8:]:
+    for cfg in CONFIGS[:5] + CONFIGS[8:]:  # incl. every bucket configuration
         configure(ix, cfg)
         gather, warps, space = cfg[:3]
         for L, k in ((1, 1), (10, 10), (37, 10), (64, 20), (200, 100)):
@@ -110,7 +112,7 @@ def test_visited_overflow_takes_exact_fallback(capi, oracle):
     ix = capi.Index(base, off, adj, 3, metric=1)
     want = oracle.search(base, off, adj, 3, q, 10, 50, metric=1)
     assert want["cmps"].max() > 256
-    for space in (1, 2, 3):
+    for space in (1, 2, 3, 4, 5):
         ix.configure(hash_log2=8, hash_space=space)
         report(f"overflow space={space}", ix.search(q, 10, 50), want)
         assert ix.last_overflow > 100
@@ -133,6 +135,24 @@ def test_hash16_displacement_exhausted(capi, oracle):
         ix.configure(hash_log2=hl, hash_space=3)
         report(f"hash16 hl={hl}", ix.search(q, 10, 80), want)
         assert lo <= ix.last_overflow <= hi
+    ix.close()
+
+
+def test_bucket16_displacement_exhausted(capi, oracle):
+    """Bucketed 16-bit visited set on a 2^20-id range with 128 buckets per query: 13 remainder bits leave 3 displacement bits
+    (6 buckets); the fullest runs exhaust them before the 70 % load limit and those queries take the exact big-table pass.
+    With 1024 buckets nothing overflows.  Eight warps split 128 buckets into 16-bucket ranges (wrap-around probing)."""
+    rng = np.random.default_rng(12)
+    n, dim = 1 << 20, 8
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((300, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 4, 12)
+    ix = capi.Index(base, off, adj, 5, metric=0)
+    want = oracle.search(base, off, adj, 5, q, 10, 80, metric=0)
+    for hl, warps, lo, hi in ((10, 2, 1, 300), (10, 8, 1, 300), (13, 2, 0, 0), (13, 1, 0, 0)):
+        ix.configure(hash_log2=hl, hash_space=4, warps_per_query=warps)
+        report(f"bucket16 hl={hl} warps={warps}", ix.search(q, 10, 80), want)
+        assert lo <= ix.last_overflow <= hi, ix.last_overflow
     ix.close()
 
 
