@@ -96,6 +96,8 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
  * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its
  * neighbours into L2, 2 = L2-prefetch the adjacency rows of scored candidates that beat it;
+ * "batch_mode": 0 auto, 1 every warp gathers the unvisited neighbours it filtered itself, 2 the hop's unvisited neighbours go to
+ * one list per query and the warps pull batches of stage_rows rows from it (what auto picks with the bucketed visited set);
  * "zero_copy" (default 1): rg_search_batch works straight on page-locked caller buffers, 0 = always stage through HBM. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Page-lock (and map) a caller-owned host buffer so that rg_search_batch can work on it without staging copies - what

@@ -171,16 +171,17 @@ class Index:
     __del__ = close
 
     def configure(self, gather=0, warps_per_query=0, ctas_per_sm=0, stage_rows=0, hash_log2=0, hash_space=0,
-                  l2_hint=None, adj_prefetch=None):
+                  l2_hint=None, adj_prefetch=None, batch_mode=0):
         _check(lib().rg_search_configure(self._h, gather, warps_per_query, ctas_per_sm, stage_rows, hash_log2))
         _check(lib().rg_search_set_option(self._h, b"hash_space", hash_space))
         if l2_hint is not None:
             _check(lib().rg_search_set_option(self._h, b"l2_hint", l2_hint))
         if adj_prefetch is not None:
             _check(lib().rg_search_set_option(self._h, b"adj_prefetch", adj_prefetch))
+        _check(lib().rg_search_set_option(self._h, b"batch_mode", batch_mode))
 
     def set_option(self, name: str, value: int):
-        """Named option of rg_search_set_option ("hash_space", "l2_hint", "adj_prefetch", "zero_copy")."""
+        """Named option of rg_search_set_option ("hash_space", "l2_hint", "adj_prefetch", "batch_mode", "zero_copy")."""
         _check(lib().rg_search_set_option(self._h, name.encode(), int(value)))
 
     @property

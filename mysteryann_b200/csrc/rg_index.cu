@@ -228,8 +228,8 @@ rg_status rg_search_configure(rg_index *ix, int gather, int warps_per_query, int
     if (gather < 0 || gather > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "gather must be 0 (auto), 1 (cp.async) or 2 (TMA bulk)");
     if (warps_per_query < 0 || warps_per_query > 8 || ctas_per_sm < 0 || ctas_per_sm > 32)
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "warps_per_query in [0,8], ctas_per_sm in [0,32]");
-    if (stage_rows < 0 || (stage_rows % 8) != 0 || stage_rows > 64)
-        return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_rows must be a multiple of 8 in [0,64]");
+    if (stage_rows < 0 || (stage_rows % 4) != 0 || stage_rows > 32)
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "stage_rows must be a multiple of 4 in [0,32]");
     if (hash_log2 != 0 && (hash_log2 < 8 || hash_log2 > 22))
         return rg::fail(RG_ERR_INVALID_ARGUMENT, "hash_log2 must be 0 (auto) or in [8,22]");
     ix->cfg_gather = gather;
@@ -248,8 +248,13 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         ix->cfg_hash_space = value;
         return RG_OK;
     }
+    if (!strcmp(name, "batch_mode")) {
+        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "batch_mode must be 0 (auto), 1 (per-warp gather lists) or 2 (one list per query, dynamic batches)");
+        ix->cfg_batch_mode = value;
+        return RG_OK;
+    }
     if (!strcmp(name, "l2_hint")) {
-        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..3");
+        if (value < 0 || value > 7) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..7");
         ix->cfg_l2_hint = value;
         return RG_OK;
     }

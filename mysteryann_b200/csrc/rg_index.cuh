@@ -43,6 +43,7 @@ struct rg_index {
     int cfg_l2_hint = 3, cfg_adj_prefetch = 3;  // see SearchParams::l2_hint / adj_prefetch; measured best on B200
                                                 // (profiles/r01_k1_variants_10m.txt)
 
+    int cfg_batch_mode = 0;  // 0 auto, 1 every warp gathers the unvisited neighbours it filtered, 2 one CTA-wide list, batches pulled dynamically
     int cfg_zero_copy = 1;  // rg_search_batch: search straight out of / into page-locked caller buffers
 
     uint64_t persist_bytes = 0;  // persisting-L2 set-aside requested so far (l2_hint bit 1)

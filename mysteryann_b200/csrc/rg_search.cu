@@ -40,7 +40,8 @@ constexpr int kMaxWarps = 8;
                           // (64 costs 4-6 % at L_pq = 55, 128 loses a third of the resident queries: profiles/r02_k1_ab_*.txt)
 #endif
 // shared control words
-enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */ };
+enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */,
+       kCtlFresh = 12 /* ids in the CTA-wide gather list */, kCtlBatch = 13 /* next batch of it */ };
 // visited-set flavours
 enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2, kHashBucket16 = 3, kHashBucket32 = 4 };
 // kHashBucket*: no atomics.  The slab is an array of buckets (16 B = 8 x 16-bit quotient entries, or 32 B = 8 x 32-bit
@@ -82,11 +83,12 @@ struct SearchParams {
                                // candidate that beats it (it will be expanded first)
     // build mode (kBuild, SearchProjectionGraphInternal src/index_bipartite.cpp:1279-1350): query w is base row
     // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
+    uint32_t shared_batches;   // 1 = the hop's unvisited ids go to one CTA-wide list and the warps pull batches of stage_rows from it
     uint32_t node_lo, exp_cap;
     uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
-    uint32_t off_pool, off_cand, off_sorted, off_pos, off_ctrl, off_hash, off_warp;
+    uint32_t off_pool, off_cand, off_sorted, off_pos, off_fresh, off_ctrl, off_hash, off_warp;
     uint32_t warp_bytes, woff_cid, woff_mine, woff_stage;  // per-warp area: [mbarrier][candidate ids][ids to filter][row staging]
 };
 
@@ -193,9 +195,8 @@ __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, con
                                                         bool active, uint32_t id, bool have_pre, const uint4 pre, uint32_t lane) {
     uint32_t tag;
     uint32_t bucket = bucket_home<kHash>(p, id, &tag), d = 0, res = 0;
-    const uint32_t dummy = 0x80000000u | lane;  // ids are < 2^31
-    const uint32_t peers = __match_any_sync(0xffffffffu, active ? id : dummy);
-    bool pending = active && (uint32_t(__ffs(peers)) - 1u == lane);  // a duplicate inside the round: its first lane decides
+    const uint32_t dummy = 0x80000000u | lane;  // ids and bucket indices are < 2^31
+    bool pending = active;
     bool need_load = !have_pre;
     uint4 s0 = pre, s1 = make_uint4(0, 0, 0, 0);
     while (__any_sync(0xffffffffu, pending)) {
@@ -213,8 +214,15 @@ __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, con
             bucket_scan32(s0, s1, want, &found, &cnt);
         }
         if (found) pending = false;
-        const bool prop = pending && cnt < 8u;
-        const uint32_t grp = __match_any_sync(0xffffffffu, prop ? bucket : dummy);
+        bool prop = pending && cnt < 8u;
+        uint32_t grp = __match_any_sync(0xffffffffu, prop ? bucket : dummy);
+        if (__any_sync(0xffffffffu, prop && (grp & (grp - 1u)) != 0u)) {
+            // several lanes append to one bucket (rare).  It may be the same id twice in the row: such lanes have walked the
+            // same buckets in lockstep, so they meet here; the first lane decides and the others report "visited"
+            const uint32_t peers = __match_any_sync(0xffffffffu, prop ? id : dummy);
+            if (prop && uint32_t(__ffs(peers)) - 1u != lane) prop = pending = false;
+            grp = __match_any_sync(0xffffffffu, prop ? bucket : dummy);
+        }
         if (prop) {
             const uint32_t slot = cnt + __popc(grp & lanemask_lt());
             if (slot < 8u) {
@@ -261,6 +269,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     uint64_t *s_cand = reinterpret_cast<uint64_t *>(smem_raw + p.off_cand);
     uint64_t *s_sorted = reinterpret_cast<uint64_t *>(smem_raw + p.off_sorted);
     uint32_t *s_pos = reinterpret_cast<uint32_t *>(smem_raw + p.off_pos);
+    uint32_t *s_fresh = reinterpret_cast<uint32_t *>(smem_raw + p.off_fresh);
     volatile uint32_t *s_ctrl = reinterpret_cast<volatile uint32_t *>(smem_raw + p.off_ctrl);
     uint32_t *s_ctrl_nv = reinterpret_cast<uint32_t *>(smem_raw + p.off_ctrl);
     unsigned char *wa = smem_raw + p.off_warp + size_t(warp) * p.warp_bytes;
@@ -349,22 +358,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         }
     };
 
-    // Gathers and scores this warp's candidates s_cid[0..n); keys below `tail` are appended to the CTA-wide list.
+    // Gathers and scores the rows s_cid[0..n) (this warp's own list, or its batch of the CTA-wide one); keys below `tail`
+    // are appended to the CTA-wide candidate list.
     // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
     // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
-    auto gather_and_score = [&](uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key, bool do_spec) {
+    auto gather_and_score = [&](const uint32_t *s_cid, uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key, bool do_spec) {
         for (uint32_t c0 = 0; c0 < n; c0 += BR) {
             const uint32_t rows = min(BR, n - c0);
             const float *stage = s_stage;
             if (kGather == 2) {
                 if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
                 __syncwarp();
-                if (rows_evict_first) {  // the gathered rows are touched once: keep them from displacing adjacency/hash lines
-                    for (uint32_t r = lane; r < rows; r += 32)
-                        bulk_g2s_hint(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar, pol_first);
-                } else {
-                    for (uint32_t r = lane; r < rows; r += 32)
-                        bulk_g2s(s_stage + size_t(r) * RS, p.base + size_t(s_cid[c0 + r]) * dim, dim * 4u, s_mbar);
+                if (lane < rows) {  // stage_rows <= 32: one row per lane
+                    float *dst = s_stage + lane * RS;
+                    const float *src = p.base + size_t(s_cid[c0 + lane]) * dim;
+                    // the gathered rows are touched once: evict_first keeps them from displacing adjacency/hash lines
+                    if (rows_evict_first) bulk_g2s_hint(dst, src, dim * 4u, s_mbar, pol_first);
+                    else bulk_g2s(dst, src, dim * 4u, s_mbar);
                 }
                 if (do_spec && c0 == 0) spec_block();
                 mbar_wait(s_mbar, mb_phase);
@@ -420,6 +430,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             s_ctrl[kCtlHop0 + 5] = 0;
             s_ctrl[kCtlHop0 + 6] = L;
             s_ctrl[kCtlHop0 + 7] = L;
+            s_ctrl[kCtlFresh] = 0;
+            s_ctrl[kCtlBatch] = 0;
         }
         __syncthreads();
         const uint32_t w = s_ctrl[kCtlWork];
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 if (kBuild && !kBucket) visit(p.ep);
             }
             __syncwarp();
-            gather_and_score(1, tail, kCtlHop0, ~0ull, false);
+            gather_and_score(s_cid, 1, tail, kCtlHop0, ~0ull, false);
         }
 
         for (;;) {
@@ -480,15 +492,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[octl + 1] = 0;
                     s_ctrl[octl + 2] = L;
                     s_ctrl[octl + 3] = L;
+                    s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
+                    s_ctrl[kCtlBatch] = 0;
                 }
                 __syncthreads();
                 start = cur + 1;
             } else {
                 // (a) position of every candidate among the pool entries; a candidate equal to a pool entry is the
                 //     re-scored entry point: "Make sure the same id isn't inserted into the set" (neighbor.h:161)
+                uint32_t lb0 = 0;  // pool position of candidate `tid` (kept for (b))
                 for (uint32_t j = tid; j < C; j += T) {
                     const uint64_t key = s_cand[j];
                     const uint32_t lo = lower_bound_key(P, size, key);
+                    if (j == tid) lb0 = lo;
                     if (lo < size && (P[lo] & ~1ull) == key) {
                         s_cand[j] = ~0ull;
                         atomicAdd(&s_ctrl_nv[ctl + 1], 1u);
@@ -501,6 +517,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[octl + 1] = 0;
                     s_ctrl[octl + 2] = L;
                     s_ctrl[octl + 3] = L;
+                    s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
+                    s_ctrl[kCtlBatch] = 0;
                 }
                 __syncthreads();
                 const uint32_t Cn = C - s_ctrl[ctl + 1];   // candidates that are really new
@@ -512,32 +530,46 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     uint32_t r = 0;
                     for (uint32_t i = 0; i < C; ++i) r += (s_cand[i] < key) ? 1u : 0u;
                     s_sorted[r] = key;
-                    s_pos[r] = lower_bound_key(P, size, key) + r;
+                    s_pos[r] = (j == tid ? lb0 : lower_bound_key(P, size, key)) + r;
                 }
                 if (have_cur && cur < minlo && tid == 0) {  // the expanded entry stays where it is
                     P[cur] |= 1ull;
                     s_ctrl[ctl + 3] = cur;
                 }
                 __syncthreads();
-                // (c) pool entries [minlo, size) shift right by the number of candidates in front of them, in place:
-                //     chunks of T entries from the top down; a chunk's new positions are >= its old ones, i.e. inside the
-                //     chunk itself (read before the barrier) or above it (already moved)
+                // (c) pool entries [minlo, size) shift right by the number of candidates in front of them, in place, in
+                //     chunks of 4T entries (four per thread, independent of each other) from the top down; a chunk's new
+                //     positions are >= its old ones, i.e. inside the chunk itself (read before the barrier) or above it
+                //     (already moved).  Candidate r stands in front of pool entry i iff its pool position s_pos[r] - r is
+                //     <= i (keys are distinct), so the shift is a binary search over 32-bit words
                 for (uint32_t hi = size; hi > minlo;) {
-                    const uint32_t lo_c = (hi - minlo > T) ? hi - T : minlo;
-                    const uint32_t i = lo_c + tid;
-                    const bool valid = i < hi;
-                    uint64_t e = 0;
-                    uint32_t pos = 0;
-                    if (valid) {
-                        e = P[i];
-                        pos = i + lower_bound_key(s_sorted, Cn, e & ~1ull);
-                        if (have_cur && i == cur) {
-                            e |= 1ull;
-                            s_ctrl[ctl + 3] = pos;
+                    const uint32_t lo_c = (hi - minlo > 4 * T) ? hi - 4 * T : minlo;
+                    uint64_t e[4];
+                    uint32_t pos[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const uint32_t i = lo_c + tid + u * T;
+                        pos[u] = L;
+                        e[u] = 0;
+                        if (i < hi) {
+                            e[u] = P[i];
+                            uint32_t a = 0, b = Cn;
+                            while (a < b) {
+                                const uint32_t mid = (a + b) >> 1;
+                                if (s_pos[mid] - mid <= i) a = mid + 1;
+                                else b = mid;
+                            }
+                            pos[u] = i + a;
+                            if (have_cur && i == cur) {
+                                e[u] |= 1ull;
+                                s_ctrl[ctl + 3] = pos[u];
+                            }
                         }
                     }
                     __syncthreads();
-                    if (valid && pos < L) P[pos] = e;
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u)
+                        if (pos[u] < L) P[pos[u]] = e[u];
                     hi = lo_c;
                 }
                 for (uint32_t r = tid; r < Cn; r += T) {
@@ -680,11 +712,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     }
                 }
             }
-            if (n_w) {
+            // a re-scored entry point lands in the lists below too; the merge drops it as a duplicate (neighbor.h:161) or the
+            // tail test drops it (neighbor.h:151), exactly like the reference
+            if (p.shared_batches) {
+                // one CTA-wide list, batches of BR rows pulled by whichever warp is free: no warp waits at the hop barrier
+                // because its share of the unvisited neighbours was larger, and only the hop's last batch is partial
+                uint32_t pos0 = 0;
+                if (lane == 0 && n_w) {
+                    pos0 = atomicAdd(&s_ctrl_nv[kCtlFresh], n_w);
+                    atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
+                }
+                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                for (uint32_t i = lane; i < n_w; i += 32) s_fresh[pos0 + i] = s_cid[i];
+                __syncthreads();
+                const uint32_t F = s_ctrl[kCtlFresh];
+                bool first = true;
+                for (;;) {
+                    uint32_t b = 0;
+                    if (lane == 0) b = atomicAdd(&s_ctrl_nv[kCtlBatch], 1u);
+                    b = __shfl_sync(0xffffffffu, b, 0) * BR;
+                    if (b >= F) break;
+                    gather_and_score(s_fresh + b, min(BR, F - b), tail, kCtlHop0 + 4 * hp, next_key, first);
+                    first = false;
+                }
+                if (first) spec_block();
+            } else if (n_w) {
                 if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
-                // a re-scored entry point lands here too; the merge drops it as a duplicate (neighbor.h:161) or the tail
-                // test drops it (neighbor.h:151), exactly like the reference
-                gather_and_score(n_w, tail, kCtlHop0 + 4 * hp, next_key, true);
+                gather_and_score(s_cid, n_w, tail, kCtlHop0 + 4 * hp, next_key, true);
             } else {
                 spec_block();
             }
@@ -800,6 +854,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.fallback = fallback ? 1u : 0u;
     p.l2_hint = uint32_t(ix->cfg_l2_hint);
     p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
+    const int batch_mode = ix->cfg_batch_mode;
     // visited set: a slab per CTA in global memory unless shared memory was asked for (hash_space 1).
     //   hash_space 0 (auto) / 4: buckets without atomics - 16-bit quotient entries (8 per 16-byte bucket) when the id range
     //                            leaves >= 3 displacement bits at no more than twice the slots, else 32-bit ids (8 per 32 B)
@@ -850,27 +905,34 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     g->slab_bytes = g->hash_kind == kHashShared ? 0
                     : (uint64_t(g->hash_kind == kHashGlobal16 || g->hash_kind == kHashBucket16 ? 2 : 4) << hl);
     const bool bucket = g->hash_kind == kHashBucket16 || g->hash_kind == kHashBucket32;
+    // one CTA-wide gather list with dynamic batches: measured no better than per-warp lists (profiles/r02_k1_sweep_buckets.txt), opt-in
+    p.shared_batches = batch_mode == 2 && W > 1 ? 1u : 0u;
 
-    uint32_t off = round_up(ix->dim * 4, 128);
+    // Shared-memory layout, packed to 16 bytes (TMA bulk destinations and LDS.128 need no more): the CTA count per SM is
+    // decided by it (12 CTAs of two warps fit up to L_pq ~ 170 at D = 200, 11 at 500).  The merge scratch (sorted candidates
+    // and their positions) aliases warp 0's row staging buffer: a merge only runs between hops, when no gather is in flight.
+    uint32_t off = round_up(ix->dim * 4, 16);
     p.off_pool = off;
-    off += round_up((L + 1) * 8, 128);
+    off += round_up((L + 1) * 8, 16);
     p.off_cand = off;
-    off += round_up(ix->adj_stride * 8, 128);
-    p.off_sorted = off;
-    off += round_up(ix->adj_stride * 8, 128);
-    p.off_pos = off;
-    off += round_up(ix->adj_stride * 4, 128);
+    off += round_up(ix->adj_stride * 8, 16);
     p.off_ctrl = off;
-    off += 128;
+    off += 64;
+    p.off_fresh = off;
+    if (p.shared_batches) off += round_up(ix->adj_stride * 4, 16);
     p.off_hash = off;
     if (g->hash_kind == kHashShared) off += (4u << hl);
     p.off_warp = off;
     // CAS flavours: a warp filters every W-th neighbour; bucket flavours: any share of the row may hash into its range
-    const uint32_t cid_cap = bucket ? round_up(ix->adj_stride, 8) : round_up((ix->adj_stride - 1 + W - 1) / W, 8);
+    const uint32_t cid_cap = bucket ? round_up(ix->adj_stride, 4) : round_up((ix->adj_stride - 1 + W - 1) / W, 4);
     p.woff_cid = 16;
     p.woff_mine = p.woff_cid + cid_cap * 4;
-    p.woff_stage = round_up(p.woff_mine + (bucket ? cid_cap * 4 : 0), 128);
-    p.warp_bytes = p.woff_stage + round_up(p.stage_rows * p.row_stride * 4, 128);
+    p.woff_stage = round_up(p.woff_mine + (bucket ? cid_cap * 4 : 0), 16);
+    const uint32_t stage_bytes = std::max<uint32_t>(round_up(p.stage_rows * p.row_stride * 4, 16),
+                                                    round_up(ix->adj_stride * 8, 16) + round_up(ix->adj_stride * 4, 16));
+    p.warp_bytes = p.woff_stage + stage_bytes;
+    p.off_sorted = p.off_warp + p.woff_stage;                       // aliases warp 0's staging rows
+    p.off_pos = p.off_sorted + round_up(ix->adj_stride * 8, 16);
     off += W * p.warp_bytes;
     g->smem_bytes = off;
     if (size_t(off) > size_t(ix->max_smem_optin))
@@ -909,19 +971,29 @@ static bool persisting_window_fits(const rg_index *ix, uint64_t bytes) {
     return bytes > 0 && bytes <= uint64_t(max_persist) && bytes <= uint64_t(max_window);
 }
 
-static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
-                                               cudaStream_t st) {
-    {   // device-wide limit shared by every index on the device
-        static std::mutex mu;
-        static uint64_t current[64] = {0};
-        std::lock_guard<std::mutex> lock(mu);
-        uint64_t &cur = current[ix->device & 63];
-        if (cur != bytes) {
-            RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(bytes)));
-            cur = bytes;
-        }
-        ix->persist_bytes = bytes;
+// Device-wide persisting-L2 set-aside, shared by every index on the device.  A launch WITHOUT a window must give it back:
+// lines that an earlier launch marked persisting stay pinned, and the set-aside stays carved out of L2, until they are
+// reset - an L_pq = 200 batch right after an L_pq = 100 batch otherwise runs with 57 MB of L2 holding dead lines.
+static std::mutex g_persist_mu;
+static uint64_t g_persist_bytes[64] = {0};
+
+static rg_status set_persisting_limit(rg_index *ix, uint64_t bytes) {
+    std::lock_guard<std::mutex> lock(g_persist_mu);
+    uint64_t &cur = g_persist_bytes[ix->device & 63];
+    if (cur != bytes) {
+        if (bytes == 0) RG_CUDA_OK(cudaCtxResetPersistingL2Cache());
+        RG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(bytes)));
+        cur = bytes;
     }
+    ix->persist_bytes = bytes;
+    return RG_OK;
+}
+
+// hit_ratio < 1: the window is larger than the set-aside and a random fraction of its lines is pinned
+static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, int grid, void *ptr, uint64_t bytes,
+                                               uint64_t limit_bytes, float hit_ratio, cudaStream_t st) {
+    rg_status s = set_persisting_limit(ix, limit_bytes);
+    if (s != RG_OK) return s;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(unsigned(grid));
@@ -933,7 +1005,7 @@ static rg_status launch_with_persisting_window(rg_index *ix, const Geometry &g, 
     attr.id = cudaLaunchAttributeAccessPolicyWindow;
     attr.val.accessPolicyWindow.base_ptr = ptr;
     attr.val.accessPolicyWindow.num_bytes = size_t(bytes);
-    attr.val.accessPolicyWindow.hitRatio = 1.0f;
+    attr.val.accessPolicyWindow.hitRatio = hit_ratio;
     attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     cfg.attrs = &attr;
@@ -1003,11 +1075,27 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
     const uint64_t slab_bytes = uint64_t(grid1) * g1.slab_bytes;
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        max_persist = max_window = 0;
+    }
     if (g1.slab_bytes && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
-        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, st);
+        uint64_t limit = slab_bytes;
+        if (const char *e = std::getenv("RG_K1_PERSIST_SLACK_PCT"))  // experiment: set-aside larger than the window
+            limit = std::min<uint64_t>(uint64_t(max_persist), slab_bytes * (100 + uint64_t(atoi(e))) / 100);
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, limit, 1.0f, st);
+        if (s != RG_OK) return s;
+    } else if (g1.slab_bytes && (ix->cfg_l2_hint & 4) && max_persist > 0 && slab_bytes <= uint64_t(max_window)) {
+        // experimental (l2_hint bit 2): slabs larger than the set-aside - pin the fraction that fits
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, uint64_t(max_persist),
+                                          float(double(max_persist) / double(slab_bytes)), st);
         if (s != RG_OK) return s;
     } else {
+        s = set_persisting_limit(ix, 0);
+        if (s != RG_OK) return s;
         g1.fn<<<grid1, g1.warps * 32, g1.smem_bytes, st>>>(g1.p);
     }
     RG_CUDA_OK(cudaGetLastError());

@@ -45,12 +45,13 @@ def capi():
 # without atomics (16-bit entries where the id range allows / 32-bit ids), 0 auto (= 4)
 CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 5, 1, 2),
            (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 4, 3, 1), (2, 1, 4, 3, 3), (2, 2, 5, 3, 3), (2, 4, 4, 0, 0),
-           (2, 8, 0, 3, 3))
+           (2, 8, 0, 3, 3), (2, 2, 4, 3, 3, 1), (2, 4, 2, 3, 3, 2), (1, 3, 3, 3, 1, 2))
 
 
 def configure(ix, cfg, **kw):
     gather, warps, space, l2, pf = cfg[:5]
-    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf, **kw)
+    bm = cfg[5] if len(cfg) > 5 else 0   # batch_mode: 0 auto, 1 per-warp gather lists, 2 one list per query
+    ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf, batch_mode=bm, **kw)
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)

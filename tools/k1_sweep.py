@@ -3,11 +3,12 @@ x beam width, CUDA-event timed with an L2 flush between repetitions.  Prints one
 gathered-row bandwidth (cmps x dim x 4 / time) and its fraction of the measured HBM peak.  A tuning aid, not the bench.
 
     python tools/k1_sweep.py --Ls 55 100 200 500 --configs w=2 w=4 w=2,hs=2 w=2,sb=2 ...
-config keys: w warps/query, hs hash_space, sr stage_rows, c ctas/SM, hl hash_log2, l2 l2_hint, pf adj_prefetch
+config keys: w warps/query, hs hash_space, sr stage_rows, c ctas/SM, hl hash_log2, l2 l2_hint, pf adj_prefetch, bm batch_mode
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 
 import torch
@@ -49,7 +50,7 @@ def main():
         kv = dict(x.split("=") for x in cfg.split(",") if x)
         g = lambda key, dflt=0: int(kv.get(key, dflt))
         ix.configure(gather=g("g"), warps_per_query=g("w"), ctas_per_sm=g("c"), stage_rows=g("sr"), hash_log2=g("hl"),
-                     hash_space=g("hs"), l2_hint=g("l2", 3), adj_prefetch=g("pf", 3))
+                     hash_space=g("hs"), l2_hint=g("l2", 3), adj_prefetch=g("pf", 3), batch_mode=g("bm"))
         for L in a.Ls:
             for _ in range(2):
                 ix.search_device(q, k, L, ids, dists, cmps, hops, None, st)
@@ -67,10 +68,15 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms += e0.elapsed_time(e1) / a.reps
+            try:  # clock / power state right after the timed repetitions (a long sweep heats the GPU up)
+                smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,temperature.gpu", "--format=csv,noheader,nounits",
+                                      "-i", "0"], capture_output=True, text=True, timeout=10).stdout.strip()
+            except Exception:
+                smi = ""
             c = float(cmps.sum().item())
             gbs = c * args.dim * 4 / (ms * 1e-3) / 1e9
             row = dict(cfg=cfg, L=L, ms=round(ms, 3), qps=round(nq / ms * 1e3), mean_cmps=round(c / nq, 1),
-                       gathered_GBs=round(gbs, 1), frac=round(gbs / peak, 4), overflow=ix.last_overflow, same_as_first_cfg=same)
+                       gathered_GBs=round(gbs, 1), frac=round(gbs / peak, 4), overflow=ix.last_overflow, same_as_first_cfg=same, smi=smi)
             rows.append(row)
             print(json.dumps(row), flush=True)
     if a.out:
