@@ -84,6 +84,14 @@ RG_API rg_status rg_search_batch(rg_index *index, const float *queries, uint64_t
 RG_API rg_status rg_search_batch_device(rg_index *index, const float *d_queries, uint64_t nq, uint32_t k,
                                         uint32_t L, uint32_t *d_ids, float *d_dists, uint32_t *d_cmps,
                                         uint32_t *d_hops, uint32_t *d_status, void *cuda_stream);
+/* Build-time beam searches (replaces IndexBipartite::SearchProjectionGraphInternal, src/index_bipartite.cpp:1279-1350, the
+ * inner loop of the connectivity enhancement :1192-1220): for every base row t in [node_lo, node_lo + count) a beam search of
+ * width L over the index's graph with row t as the query - the entry point is scored and marked visited, neighbour t itself is
+ * never scored - recording the EXPANDED nodes in expansion order (the reference's full_retset).  d_exp_keys[count][exp_cap]
+ * receives (monotone image of the FP32 distance) << 32 | id << 1, d_exp_cnt[count] min(#expanded, exp_cap).  Device buffers,
+ * enqueued on cuda_stream.  rg_build_roargraph_device runs these in waves; the entry is exported for parity tests. */
+RG_API rg_status rg_search_expanded_device(rg_index *index, uint32_t node_lo, uint64_t count, uint32_t L,
+                                           uint64_t *d_exp_keys, uint32_t *d_exp_cnt, uint32_t exp_cap, void *cuda_stream);
 /* Tuning knobs (0 = automatic): see DESIGN.md "K1".  gather: 1 cp.async (LDGSTS), 2 TMA bulk copy (cp.async.bulk +
  * mbarrier); warps_per_query: warps of the CTA that owns a query (1..8); stage_rows: rows per warp staging buffer. */
 RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_query, int ctas_per_sm, int stage_rows,
@@ -97,7 +105,8 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
  * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its
  * neighbours into L2, 2 = L2-prefetch the adjacency rows of scored candidates that beat it;
  * "batch_mode": 0 auto, 1 every warp gathers the unvisited neighbours it filtered itself, 2 the hop's unvisited neighbours go to
- * one list per query and the warps pull batches of stage_rows rows from it (what auto picks with the bucketed visited set);
+ * one list per query and the warps pull batches of stage_rows rows from it, 3 per-warp lists handed out in batches, a warp
+ * that has emptied its own takes batches of the others';
  * "zero_copy" (default 1): rg_search_batch works straight on page-locked caller buffers, 0 = always stage through HBM. */
 RG_API rg_status rg_search_set_option(rg_index *index, const char *name, int value);
 /* Page-lock (and map) a caller-owned host buffer so that rg_search_batch can work on it without staging copies - what
@@ -107,6 +116,9 @@ RG_API rg_status rg_host_register(void *ptr, uint64_t bytes);
 RG_API rg_status rg_host_unregister(void *ptr);
 /* Diagnostics (synchronises the device): queries of the last batch that were redone by the big-table visited-set pass. */
 RG_API uint32_t rg_search_last_overflow_count(rg_index *index);
+/* Diagnostics (synchronises the device): ids of the last batch that went to a warp's shared-memory exception list because
+ * their probe window in the bucketed visited set was full (exact either way; see DESIGN.md "K1"). */
+RG_API uint32_t rg_search_last_exception_count(rg_index *index);
 /* Number of kernel launches issued by this library on behalf of `index` so far. */
 RG_API uint64_t rg_index_launch_count(const rg_index *index);
 

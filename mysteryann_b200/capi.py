@@ -20,7 +20,7 @@ RG_ERR_NO_DEVICE = 5
 METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 4
 
 SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_index_create", "rg_index_destroy",
-           "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count",
+           "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_expanded_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count", "rg_search_last_exception_count",
            "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
            "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
@@ -58,6 +58,8 @@ def lib():
     L.rg_search_batch.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp]
     L.rg_search_batch_device.restype = i32
     L.rg_search_batch_device.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp, vp, vp]
+    L.rg_search_expanded_device.restype = i32
+    L.rg_search_expanded_device.argtypes = [vp, u32, u64, u32, vp, vp, u32, vp]
     L.rg_search_configure.restype = i32
     L.rg_search_configure.argtypes = [vp, i32, i32, i32, i32, i32]
     L.rg_search_set_option.restype = i32
@@ -68,6 +70,8 @@ def lib():
     L.rg_search_set_option.argtypes = [vp, C.c_char_p, i32]
     L.rg_search_last_overflow_count.restype = u32
     L.rg_search_last_overflow_count.argtypes = [vp]
+    L.rg_search_last_exception_count.restype = u32
+    L.rg_search_last_exception_count.argtypes = [vp]
     L.rg_index_launch_count.restype = u64
     L.rg_index_launch_count.argtypes = [vp]
     L.rg_knn_exact.restype = i32
@@ -189,6 +193,10 @@ class Index:
         return int(lib().rg_search_last_overflow_count(self._h))
 
     @property
+    def last_exceptions(self) -> int:
+        return int(lib().rg_search_last_exception_count(self._h))
+
+    @property
     def launches(self) -> int:
         return int(lib().rg_index_launch_count(self._h))
 
@@ -216,6 +224,21 @@ class Index:
         p = lambda t: None if t is None else t.data_ptr()
         _check(lib().rg_search_batch_device(self._h, p(d_queries), nq, k, L, p(d_ids), p(d_dists), p(d_cmps),
                                             p(d_hops), p(d_status), stream))
+
+    def search_expanded(self, node_lo, count, L, cap):
+        """Build-time beam searches of base rows [node_lo, node_lo + count) (rg_search_expanded_device): returns
+        (ids [count, cap] uint32, dists [count, cap] float32, counts [count]) of the expanded nodes in expansion order."""
+        import torch
+
+        keys = torch.zeros((count, cap), dtype=torch.int64, device=f"cuda:{self.device}")
+        cnt = torch.zeros(count, dtype=torch.int32, device=f"cuda:{self.device}")
+        _check(lib().rg_search_expanded_device(self._h, node_lo, count, L, keys.data_ptr(), cnt.data_ptr(), cap, None))
+        torch.cuda.synchronize()
+        k = keys.cpu().numpy().view(np.uint64)
+        ids = ((k >> np.uint64(1)) & np.uint64(0x7FFFFFFF)).astype(np.uint32)
+        o = (k >> np.uint64(32)).astype(np.uint32)                       # monotone image of the FP32 distance
+        bits = np.where(o & np.uint32(0x80000000), o & np.uint32(0x7FFFFFFF), ~o)
+        return ids, bits.astype(np.uint32).view(np.float32), cnt.cpu().numpy().view(np.uint32)
 
 
 class Graph:

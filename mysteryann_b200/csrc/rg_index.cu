@@ -249,7 +249,7 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         return RG_OK;
     }
     if (!strcmp(name, "batch_mode")) {
-        if (value < 0 || value > 2) return rg::fail(RG_ERR_INVALID_ARGUMENT, "batch_mode must be 0 (auto), 1 (per-warp gather lists) or 2 (one list per query, dynamic batches)");
+        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "batch_mode must be 0 (auto), 1 (per-warp gather lists), 2 (one list per query, dynamic batches) or 3 (per-warp lists, idle warps take batches of the others)");
         ix->cfg_batch_mode = value;
         return RG_OK;
     }

@@ -32,7 +32,7 @@
 
 namespace rg {
 
-enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4 };
+enum { kCntWork = 0, kCntNotEnough = 1, kCntOverflow = 2, kCntFatal = 3, kCntWork2 = 4, kCntException = 5 };
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kMaxWarps = 8;
 #ifndef RG_K1_MIN_CTAS
@@ -41,7 +41,8 @@ constexpr int kMaxWarps = 8;
 #endif
 // shared control words
 enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */,
-       kCtlFresh = 12 /* ids in the CTA-wide gather list */, kCtlBatch = 13 /* next batch of it */ };
+       kCtlFresh = 12 /* ids in the CTA-wide gather list */, kCtlBatch = 13 /* next batch of it */,
+       kCtlPub0 = 16 /* per warp: 1 + length of its gather list once it is complete */, kCtlNext0 = 24 /* per warp: next batch */ };
 // visited-set flavours
 enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2, kHashBucket16 = 3, kHashBucket32 = 4 };
 // kHashBucket*: no atomics.  The slab is an array of buckets (16 B = 8 x 16-bit quotient entries, or 32 B = 8 x 32-bit
@@ -72,7 +73,9 @@ struct SearchParams {
     // 16-bit quotient entries (kHashGlobal16): x = (id * h16_mult) mod 2^h16_bits is a bijection of the id range; the home
     // slot is its top hash_log2 bits, the entry stores the remaining h16_rbits bits and the probe displacement
     uint32_t h16_bits, h16_rbits, h16_dbits, h16_maxd, h16_mult;
-    uint32_t bkt_log2;         // kHashBucket*: log2(number of buckets); h16_* then describe the bucket-level quotient
+    uint32_t nb, nb_per_warp;  // kHashBucket*: buckets per query (any multiple of W) and per warp; h16_* then describe the
+                               // bucket-level quotient (h16_rbits = entry bits taken from x)
+    uint32_t slab_words;       // kHashBucket*: 32-bit words per slab
     uint32_t stage_rows;       // rows per warp staging buffer (multiple of 8)
     uint32_t row_stride;       // floats between staged rows; row_stride % 32 == 16 -> conflict-free float4 reads
     uint32_t chunk_magic;      // ceil(2^32 / (dim/4)) for the cp.async index split
@@ -84,12 +87,13 @@ struct SearchParams {
     // build mode (kBuild, SearchProjectionGraphInternal src/index_bipartite.cpp:1279-1350): query w is base row
     // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
     uint32_t shared_batches;   // 1 = the hop's unvisited ids go to one CTA-wide list and the warps pull batches of stage_rows from it
+    uint32_t steal_batches;    // 1 = per-warp lists; a warp that has finished its own takes batches of the others' (no extra barrier)
     uint32_t node_lo, exp_cap;
     uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
     uint32_t off_pool, off_cand, off_sorted, off_pos, off_fresh, off_ctrl, off_hash, off_warp;
-    uint32_t warp_bytes, woff_cid, woff_mine, woff_stage;  // per-warp area: [mbarrier][candidate ids][ids to filter][row staging]
+    uint32_t warp_bytes, woff_cid, woff_mine, woff_exc, woff_stage;  // per-warp area: [mbarrier][candidate ids][ids to filter][exception list][row staging]
 };
 
 // ---- exact visited set --------------------------------------------------------------------------
@@ -148,16 +152,25 @@ __device__ __forceinline__ uint4 ld_cg_v4(const void *ptr) {  // L2-only vector 
     asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
     return v;
 }
-// home bucket of an id and the part of the entry that does not depend on the displacement
+// Home bucket of an id, the warp that owns it and the part of the entry that does not depend on the displacement.  The
+// bucket count nb is ANY multiple of W, so a slab is as large as the beam width needs and not the next power of two (which
+// decides whether the slabs of all resident queries fit L2).  16-bit flavour: x = id * M mod 2^B is a bijection of the id
+// range; with a = x / 2^B in [0, 1) the home bucket is floor(a * nb) and the owner floor(a * W) = home / (nb / W).  The x
+// values of one bucket are a contiguous run of at most ceil(2^B / nb) <= 2^rbits numbers, so x mod 2^rbits tells them
+// apart: that is what the entry stores - no division anywhere.
 template <int kHash>
-__device__ __forceinline__ uint32_t bucket_home(const SearchParams &p, uint32_t id, uint32_t *tag) {
+__device__ __forceinline__ uint32_t bucket_home(const SearchParams &p, uint32_t id, uint32_t W, uint32_t *owner, uint32_t *tag) {
     if (kHash == kHashBucket16) {
         const uint32_t x = (id * p.h16_mult) & ((1u << p.h16_bits) - 1u);
+        const uint32_t a = x << (32 - p.h16_bits);
         *tag = (x & ((1u << p.h16_rbits) - 1u)) << p.h16_dbits;
-        return x >> p.h16_rbits;
+        *owner = __umulhi(a, W);
+        return __umulhi(a, p.nb);
     }
+    const uint32_t a = id * 0x9E3779B1u;
     *tag = id;
-    return (id * 0x9E3779B1u) >> (32 - p.bkt_log2);
+    *owner = __umulhi(a, W);
+    return __umulhi(a, p.nb);
 }
 __device__ __forceinline__ void bucket_scan16(const uint4 s, uint32_t want, bool *found, uint32_t *cnt) {
     const uint32_t w[4] = {s.x, s.y, s.z, s.w};
@@ -190,11 +203,18 @@ __device__ __forceinline__ void bucket_scan32(const uint4 a, const uint4 b, uint
 // for the entry, count the used slots; lanes that want to append to the same bucket take consecutive slots in lane order
 // (match.any); whoever finds the bucket full moves to the next one (displacement + 1) and sees this round's stores there
 // because __syncwarp orders them before the next round's loads.
+// An id whose whole probe window (home bucket + displacement range) is full goes to a small per-warp EXCEPTION LIST in
+// shared memory (s_exc[0] = count, then ids).  With 13-bit remainders only 3 displacement bits are left, and although a run
+// of 7 full buckets is a 1e-8 event per insert at load 0.5, a 10 000-query batch at L_pq = 200 makes 1e8 inserts: the two
+// to six queries per batch that hit it used to be re-run from scratch by the big-table pass after the launch (5-18 % of
+// the batch time).  A later lookup of such an id walks the same full window, ends here too and finds it in the list.
+constexpr uint32_t kExcCap = 15;
 template <int kHash>
 __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, const SearchParams &p, uint32_t blo, uint32_t bhi,
-                                                        bool active, uint32_t id, bool have_pre, const uint4 pre, uint32_t lane) {
-    uint32_t tag;
-    uint32_t bucket = bucket_home<kHash>(p, id, &tag), d = 0, res = 0;
+                                                        bool active, uint32_t id, bool have_pre, const uint4 pre, uint32_t lane,
+                                                        uint32_t *s_exc) {
+    uint32_t tag, owner;
+    uint32_t bucket = bucket_home<kHash>(p, id, 1u, &owner, &tag), d = 0, res = 0;
     const uint32_t dummy = 0x80000000u | lane;  // ids and bucket indices are < 2^31
     bool pending = active;
     bool need_load = !have_pre;
@@ -234,7 +254,7 @@ __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, con
         }
         if (pending) {  // bucket full
             if (++d > p.h16_maxd) {
-                res = 2u;
+                res = 3u;  // probe window exhausted: exception list, below
                 pending = false;
             } else {
                 bucket = (bucket + 1u == bhi) ? blo : bucket + 1u;
@@ -242,6 +262,24 @@ __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, con
             }
         }
         __syncwarp();
+    }
+    uint32_t exc = __ballot_sync(0xffffffffu, res == 3u);
+    while (exc) {  // cold: one lane at a time
+        const uint32_t src = __ffs(exc) - 1u;
+        const uint32_t eid = __shfl_sync(0xffffffffu, id, src);
+        const uint32_t n_exc = s_exc[0];
+        const bool hit = __any_sync(0xffffffffu, lane < n_exc && s_exc[1 + lane] == eid);
+        if (lane == src) {
+            if (hit) res = 0u;
+            else if (n_exc < kExcCap) {
+                s_exc[1 + n_exc] = eid;
+                s_exc[0] = n_exc + 1u;
+                res = 1u;
+                atomicAdd(&p.counters[kCntException], 1u);  // diagnostics
+            } else res = 2u;  // the list is full as well: big-table pass
+        }
+        __syncwarp();
+        exc &= exc - 1u;
     }
     return res;
 }
@@ -278,14 +316,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
     float *s_stage = reinterpret_cast<float *>(wa + p.woff_stage);
     constexpr bool kBucket = kHash == kHashBucket16 || kHash == kHashBucket32;
     uint32_t *s_mine = reinterpret_cast<uint32_t *>(wa + p.woff_mine);  // bucket flavours: ids of the expanded row this warp owns
+    uint32_t *s_exc = reinterpret_cast<uint32_t *>(wa + p.woff_exc);    // bucket flavours: exception list (see bucket_test_and_set)
     uint32_t *hash32 = kHash == kHashShared ? reinterpret_cast<uint32_t *>(smem_raw + p.off_hash)
-                       : kBucket            ? p.ghash + (size_t(blockIdx.x) << (p.bkt_log2 + (kHash == kHashBucket16 ? 2 : 3)))
+                       : kBucket            ? p.ghash + size_t(blockIdx.x) * p.slab_words
                                             : p.ghash + (size_t(blockIdx.x) << (kHash == kHashGlobal16 ? p.hash_log2 - 1 : p.hash_log2));
     unsigned short *hash16 = reinterpret_cast<unsigned short *>(hash32);
     unsigned char *slab = reinterpret_cast<unsigned char *>(hash32);
-    // bucket flavours: this warp's bucket range (home buckets with floor(home * W / buckets) == warp)
-    const uint32_t blo = kBucket ? uint32_t(((uint64_t(warp) << p.bkt_log2) + W - 1) / W) : 0u;
-    const uint32_t bhi = kBucket ? uint32_t(((uint64_t(warp + 1) << p.bkt_log2) + W - 1) / W) : 0u;
+    // bucket flavours: this warp's bucket range
+    const uint32_t blo = kBucket ? warp * p.nb_per_warp : 0u;
+    const uint32_t bhi = kBucket ? blo + p.nb_per_warp : 0u;
 
     const uint32_t dim = p.dim, n16 = dim >> 4;
     const bool tail8 = (dim & 15u) != 0;
@@ -328,8 +367,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             else if (it == 2) word = wr[2];
             else word = (idx < deg) ? __ldg(row + 1 + idx) : kEmpty;
             bool mine = idx < deg && !(kBuild && word == self);
-            uint32_t tag;
-            if (mine) mine = ((bucket_home<kHash>(p, word, &tag) * W) >> p.bkt_log2) == warp;
+            uint32_t tag, owner = W;
+            if (mine) bucket_home<kHash>(p, word, W, &owner, &tag);
+            mine = owner == warp;
             const uint32_t m = __ballot_sync(0xffffffffu, mine);
             if (mine) s_mine[n + __popc(m & lanemask_lt())] = word;
             n += __popc(m);
@@ -347,8 +387,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         }
         spec_n = compact_mine(nullptr, spec_deg, sreg);
         for (uint32_t i = lane; i < spec_n; i += 32) {
-            uint32_t tag;
-            const uint32_t b = bucket_home<kHash>(p, s_mine[i], &tag);
+            uint32_t tag, owner;
+            const uint32_t b = bucket_home<kHash>(p, s_mine[i], 1u, &owner, &tag);
             if (kHash == kHashBucket16) {
                 if (RG_K1_SPEC_SECTOR_REGS && i < 32) spec_sec = ld_cg_v4(slab + (size_t(b) << 4));
                 else prefetch_l2(slab + (size_t(b) << 4));
@@ -433,6 +473,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             s_ctrl[kCtlFresh] = 0;
             s_ctrl[kCtlBatch] = 0;
         }
+        if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;  // publication words and batch counters of the W <= 8 warps
+        if (kBucket && lane == 0) s_exc[0] = 0;
         __syncthreads();
         const uint32_t w = s_ctrl[kCtlWork];
         const uint32_t nwork = p.fallback ? min(p.counters[kCntOverflow], p.nq) : p.nq;
@@ -446,8 +488,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             for (uint32_t i = tid; i < cpr; i += T) dst[i] = src[i];
             uint4 *h4 = reinterpret_cast<uint4 *>(hash32);
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            const uint32_t n_vec = kBucket ? 1u << (p.bkt_log2 + (kHash == kHashBucket16 ? 0 : 1))
-                                           : 1u << (p.hash_log2 - (kHash == kHashGlobal16 ? 3 : 2));
+            const uint32_t n_vec = kBucket ? p.slab_words >> 2 : 1u << (p.hash_log2 - (kHash == kHashGlobal16 ? 3 : 2));
             for (uint32_t i = tid; i < n_vec; i += T) h4[i] = e4;
         }
         __syncthreads();
@@ -461,9 +502,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         // search does mark it (:1309)
         self = p.node_lo + qi;
         if (kBuild && kBucket) {  // every warp takes part; the owner of the entry point's home bucket inserts it
-            uint32_t tag;
-            const bool act = lane == 0 && ((bucket_home<kHash>(p, p.ep, &tag) * W) >> p.bkt_log2) == warp;
-            bucket_test_and_set<kHash>(slab, p, blo, bhi, act, p.ep, false, spec_sec, lane);
+            uint32_t tag, owner;
+            bucket_home<kHash>(p, p.ep, W, &owner, &tag);
+            const bool act = lane == 0 && owner == warp;
+            bucket_test_and_set<kHash>(slab, p, blo, bhi, act, p.ep, false, spec_sec, lane, s_exc);
         }
         if (warp == 0) {
             if (lane == 0) {
@@ -495,6 +537,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
                     s_ctrl[kCtlBatch] = 0;
                 }
+                if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
                 __syncthreads();
                 start = cur + 1;
             } else {
@@ -520,6 +563,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
                     s_ctrl[kCtlBatch] = 0;
                 }
+                if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
                 __syncthreads();
                 const uint32_t Cn = C - s_ctrl[ctl + 1];   // candidates that are really new
                 const uint32_t minlo = min(s_ctrl[ctl + 2], size);  // pool entries in front of it do not move
@@ -665,7 +709,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     const bool act = r0 + lane < n_mine;
                     const uint32_t id = act ? s_mine[r0 + lane] : 0u;
                     const bool pre = RG_K1_SPEC_SECTOR_REGS && kHash == kHashBucket16 && spec_hit && r0 == 0;
-                    uint32_t v = bucket_test_and_set<kHash>(slab, p, blo, bhi, act, id, pre, spec_sec, lane);
+                    uint32_t v = bucket_test_and_set<kHash>(slab, p, blo, bhi, act, id, pre, spec_sec, lane, s_exc);
                     if (v == 2u) {
                         s_ctrl[kCtlHashFull] = 1;
                         v = 0;
@@ -734,6 +778,37 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     if (b >= F) break;
                     gather_and_score(s_fresh + b, min(BR, F - b), tail, kCtlHop0 + 4 * hp, next_key, first);
                     first = false;
+                }
+                if (first) spec_block();
+            } else if (p.steal_batches) {
+                // per-warp lists with work stealing: every list is handed out in batches of BR rows through a counter; a warp
+                // that has emptied its own list takes batches of the other warps' lists (once those are published), so
+                // nobody waits at the hop barrier because its share of the unvisited neighbours was a batch shorter
+                if (lane == 0) {
+                    if (n_w) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
+                    __threadfence_block();  // the list (written before the __syncwarp above) before its length
+                    s_ctrl[kCtlPub0 + warp] = n_w + 1u;
+                }
+                bool first = true;
+                for (uint32_t v = 0; v < W; ++v) {
+                    const uint32_t vw = warp + v < W ? warp + v : warp + v - W;
+                    uint32_t n_v = n_w;
+                    if (v) {
+                        uint32_t pub = 0;
+                        if (lane == 0) pub = s_ctrl[kCtlPub0 + vw];
+                        pub = __shfl_sync(0xffffffffu, pub, 0);
+                        if (pub <= BR + 1u) continue;  // not published yet, or a single batch that its owner is working on
+                        n_v = pub - 1u;
+                    }
+                    const uint32_t *list = reinterpret_cast<const uint32_t *>(smem_raw + p.off_warp + size_t(vw) * p.warp_bytes + p.woff_cid);
+                    for (;;) {
+                        uint32_t b = 0;
+                        if (lane == 0) b = atomicAdd(&s_ctrl_nv[kCtlNext0 + vw], 1u);
+                        b = __shfl_sync(0xffffffffu, b, 0) * BR;
+                        if (b >= n_v) break;
+                        gather_and_score(list + b, min(BR, n_v - b), tail, kCtlHop0 + 4 * hp, next_key, first);
+                        first = false;
+                    }
                 }
                 if (first) spec_block();
             } else if (n_w) {
@@ -866,27 +941,40 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     while ((1ull << id_bits) < ix->n && id_bits < 31) ++id_bits;
     const bool want_bucket = global_hash && !fallback && (space == 0 || space == 4 || space == 5);
     p.hash_limit = 0;
+    uint64_t bucket_slab_bytes = 0;
     if (want_bucket) {
-        hl = std::max<uint32_t>(hl, 6u);
-        const uint32_t hb = hl - 3;                                                      // 8 entries per bucket
-        const uint32_t hb16 = std::max<uint32_t>(hb, id_bits > 13 ? id_bits - 13 : 0);  // remainder <= 13 bits
-        if (space != 5 && allow16 && hb16 <= hb + 1 && hb16 <= 19) {
+        // slots wanted: load <= 0.4 at the usual number of visited nodes (auto_hash_log2 rounds this up to a power of two
+        // for the atomicCAS tables; the buckets take it as it is)
+        const double want = ix->cfg_hash_log2 ? double(1u << ix->cfg_hash_log2) : (1000.0 + 30.0 * L) / 0.4;
+        const uint32_t nbw = std::max<uint32_t>(uint32_t((want + 7.0) / 8.0), 8u);           // 8 entries per bucket
+        const uint32_t min_nb16 = id_bits > 13 ? 1u << (id_bits - 13) : 1u;                   // entry keeps <= 13 bits of x
+        const uint32_t nb16 = std::max(nbw, min_nb16);
+        if (space != 5 && allow16 && nb16 <= 2 * nbw && nb16 <= (1u << 19)) {
             g->hash_kind = kHashBucket16;
-            p.bkt_log2 = hb16;
-            hl = hb16 + 3;
-            p.h16_bits = std::max(id_bits, hb16);
-            p.h16_rbits = p.h16_bits - hb16;
+            p.nb = round_up(nb16, W);
+            p.h16_bits = id_bits;
+            const uint64_t run = ((1ull << id_bits) + p.nb - 1) / p.nb;  // x values per bucket
+            p.h16_rbits = 0;
+            while ((1ull << p.h16_rbits) < run) ++p.h16_rbits;
             p.h16_dbits = std::min<uint32_t>(16u - p.h16_rbits, 8u);
             p.h16_maxd = (1u << p.h16_dbits) - 2u;  // all-ones is kept for the empty entry
             p.h16_mult = (uint32_t(double(1ull << p.h16_bits) * 0.6180339887498949) | 1u) & uint32_t((1ull << p.h16_bits) - 1);
+            bucket_slab_bytes = uint64_t(p.nb) * 16;
         } else {
             g->hash_kind = kHashBucket32;
-            p.bkt_log2 = hb;
+            p.nb = round_up(nbw, W);
             p.h16_maxd = 30;
+            bucket_slab_bytes = uint64_t(p.nb) * 32;
         }
-        // the smallest per-warp bucket range must stay longer than the longest probe walk
-        p.h16_maxd = std::min<uint32_t>(p.h16_maxd, std::max<uint32_t>(1u, ((1u << p.bkt_log2) / W) - 1u));
-        p.hash_limit = uint32_t((uint64_t(1) << hl) * 70 / 100);
+        p.nb_per_warp = p.nb / W;
+        p.slab_words = uint32_t(bucket_slab_bytes / 4);
+        // a warp's bucket range must stay longer than the longest probe walk
+        p.h16_maxd = std::min<uint32_t>(p.h16_maxd, std::max<uint32_t>(1u, p.nb_per_warp - 1u));
+        // The load limit only keeps probe walks short; what a bucket table cannot take shows up as an exhausted displacement
+        // field (the insert reports it and the query goes to the big-table pass).  That pass re-runs a query from scratch
+        // after the primary launch - four queries of 10 000 cost 18 % at L_pq = 200 - so heavy queries may fill the table to
+        // 90 % before they are handed over (at 70 % the 4 heaviest of 10 000 were: 1.4x the mean number of visited nodes).
+        p.hash_limit = uint32_t(uint64_t(p.nb) * 8 * 90 / 100);
     } else if (global_hash && !fallback && space != 2 && allow16) {
         const uint32_t h16 = std::max<uint32_t>(hl, id_bits > 10 ? id_bits - 10 : 0);  // >= 6 displacement bits
         if (h16 <= hl + 1 && h16 <= 22) {
@@ -903,10 +991,12 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.hash_log2 = hl;
     if (!p.hash_limit) p.hash_limit = uint32_t((uint64_t(1) << hl) * 85 / 100);
     g->slab_bytes = g->hash_kind == kHashShared ? 0
-                    : (uint64_t(g->hash_kind == kHashGlobal16 || g->hash_kind == kHashBucket16 ? 2 : 4) << hl);
+                    : bucket_slab_bytes     ? bucket_slab_bytes
+                                            : (uint64_t(g->hash_kind == kHashGlobal16 ? 2 : 4) << hl);
     const bool bucket = g->hash_kind == kHashBucket16 || g->hash_kind == kHashBucket32;
     // one CTA-wide gather list with dynamic batches: measured no better than per-warp lists (profiles/r02_k1_sweep_buckets.txt), opt-in
     p.shared_batches = batch_mode == 2 && W > 1 ? 1u : 0u;
+    p.steal_batches = batch_mode == 3 && W > 1 ? 1u : 0u;
 
     // Shared-memory layout, packed to 16 bytes (TMA bulk destinations and LDS.128 need no more): the CTA count per SM is
     // decided by it (12 CTAs of two warps fit up to L_pq ~ 170 at D = 200, 11 at 500).  The merge scratch (sorted candidates
@@ -917,7 +1007,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.off_cand = off;
     off += round_up(ix->adj_stride * 8, 16);
     p.off_ctrl = off;
-    off += 64;
+    off += 128;
     p.off_fresh = off;
     if (p.shared_batches) off += round_up(ix->adj_stride * 4, 16);
     p.off_hash = off;
@@ -927,7 +1017,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     const uint32_t cid_cap = bucket ? round_up(ix->adj_stride, 4) : round_up((ix->adj_stride - 1 + W - 1) / W, 4);
     p.woff_cid = 16;
     p.woff_mine = p.woff_cid + cid_cap * 4;
-    p.woff_stage = round_up(p.woff_mine + (bucket ? cid_cap * 4 : 0), 16);
+    p.woff_exc = p.woff_mine + (bucket ? cid_cap * 4 : 0);
+    p.woff_stage = round_up(p.woff_exc + (bucket ? (kExcCap + 1) * 4 : 0), 16);
     const uint32_t stage_bytes = std::max<uint32_t>(round_up(p.stage_rows * p.row_stride * 4, 16),
                                                     round_up(ix->adj_stride * 8, 16) + round_up(ix->adj_stride * 4, 16));
     p.warp_bytes = p.woff_stage + stage_bytes;
@@ -1134,6 +1225,25 @@ rg_status rg_search_batch_device(rg_index *ix, const float *d_queries, uint64_t 
     rg::DeviceGuard guard(ix->device);
     return rg::search_device(ix, d_queries, nq, k, L, d_ids, d_dists, d_cmps, d_hops, d_status,
                              static_cast<cudaStream_t>(cuda_stream));
+}
+
+rg_status rg_search_expanded_device(rg_index *ix, uint32_t node_lo, uint64_t count, uint32_t L, uint64_t *d_exp_keys,
+                                    uint32_t *d_exp_cnt, uint32_t exp_cap, void *cuda_stream) {
+    if (!ix || !d_exp_keys || !d_exp_cnt || exp_cap == 0)
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_expanded_device: null argument");
+    if (uint64_t(node_lo) + count > ix->n) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_search_expanded_device: rows out of range");
+    rg::DeviceGuard guard(ix->device);
+    return rg::search_expanded_device(ix, node_lo, count, L, d_exp_keys, d_exp_cnt, exp_cap, static_cast<cudaStream_t>(cuda_stream));
+}
+
+// diagnostics: ids of the last batch that went to a warp's exception list (bucketed visited set, probe window exhausted)
+uint32_t rg_search_last_exception_count(rg_index *ix) {
+    if (!ix) return 0;
+    rg::DeviceGuard guard(ix->device);
+    uint32_t v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(&v, ix->d_counters + rg::kCntException, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return v;
 }
 
 // diagnostics: queries of the last batch whose visited set outgrew the primary table and were redone by the big-table pass

@@ -62,6 +62,10 @@ class Oracle:
         lib.rgo_search_roargraph.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rgo_search_projection_internal.restype = C.c_int
+        lib.rgo_search_projection_internal.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                                       C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rgo_exact_knn.restype = C.c_int
         lib.rgo_exact_knn.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                       C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -95,6 +99,17 @@ class Oracle:
                                            nq, k, L, threads or self.num_procs(), _ptr(ids), _ptr(dists),
                                            _ptr(cmps), _ptr(hops), C.byref(sec))
         return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, seconds=sec.value, rc=rc)
+
+    def search_expanded(self, base, offsets, adj, ep, node_lo, count, L, cap, metric=1, threads=None):
+        """Build-time beam searches (SearchProjectionGraphInternal): expanded (ids, dists, count) per target row."""
+        base = np.ascontiguousarray(base, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.uint64); adj = np.ascontiguousarray(adj, np.uint32)
+        n, d = base.shape
+        ids = np.zeros((count, cap), np.uint32); dists = np.zeros((count, cap), np.float32)
+        cnt = np.zeros(count, np.uint32)
+        self.lib.rgo_search_projection_internal(_ptr(base), n, d, metric, _ptr(offsets), _ptr(adj), ep, node_lo, count, L, cap,
+                                                threads or self.num_procs(), _ptr(ids), _ptr(dists), _ptr(cnt))
+        return ids, dists, cnt
 
     def exact_knn(self, base, queries, K, metric=1, part_size=0, threads=None):
         base = np.ascontiguousarray(base, np.float32); queries = np.ascontiguousarray(queries, np.float32)

@@ -248,6 +248,51 @@ int rgo_search_roargraph(const float *base, uint64_t n, uint32_t dim, int metric
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * IndexBipartite::SearchProjectionGraphInternal, src/index_bipartite.cpp:1279-1350: the beam search of the connectivity
+ * enhancement (:1192-1220).  The query is base row tgt; the entry point is scored, inserted and marked visited (:1302-1312);
+ * every closest_unexpanded node is appended to full_retset (:1318) before its neighbours are visited; a neighbour equal to
+ * tgt or already visited is skipped (:1326), the rest are marked, scored and inserted (:1332-1345).  Output: the first
+ * `cap` expanded (id, distance) pairs per target and min(#expanded, cap).  (No compiled-reference pin for this function:
+ * it is a private member working on the builder's internal supply_nbrs_; its parts - pool, distance - are pinned.)
+ * ---------------------------------------------------------------------------------------------- */
+int rgo_search_projection_internal(const float *base, uint64_t n, uint32_t dim, int metric, const uint64_t *adj_offsets,
+                                   const uint32_t *adj, uint32_t ep, uint32_t node_lo, uint64_t count, uint32_t L,
+                                   uint32_t cap, int num_threads, uint32_t *exp_ids, float *exp_dists, uint32_t *exp_cnt) {
+    if (num_threads < 1) num_threads = 1;
+#pragma omp parallel num_threads(num_threads)
+    {
+        uint8_t *visited = (uint8_t *)malloc(n);
+        rgo_pool q;
+        pool_init(&q, L);
+#pragma omp for schedule(dynamic, 1)
+        for (uint64_t t = 0; t < count; ++t) {
+            const uint32_t tgt = node_lo + (uint32_t)t;
+            const float *query = base + (uint64_t)tgt * dim;
+            memset(visited, 0, n);
+            q.size = 0; q.cur = 0;
+            pool_insert(&q, ep, rgo_distance(metric, base + (uint64_t)ep * dim, query, dim)); /* :1305-1310 */
+            visited[ep] = 1;                                                                  /* :1311 */
+            uint32_t h = 0;
+            while (pool_has_unexpanded(&q)) {                                                 /* :1315 */
+                rgo_neighbor cur = pool_closest_unexpanded(&q);                               /* :1317 */
+                if (h < cap) { exp_ids[t * cap + h] = cur.id; exp_dists[t * cap + h] = cur.distance; } /* :1319 */
+                ++h;
+                for (uint64_t j = adj_offsets[cur.id]; j < adj_offsets[cur.id + 1]; ++j) {    /* :1325 */
+                    uint32_t nbr = adj[j];
+                    if (visited[nbr] || nbr == tgt) continue;                                 /* :1328 */
+                    visited[nbr] = 1;                                                         /* :1333 */
+                    pool_insert(&q, nbr, rgo_distance(metric, base + (uint64_t)nbr * dim, query, dim)); /* :1335-1345 */
+                }
+            }
+            exp_cnt[t] = h < cap ? h : cap;
+        }
+        pool_free(&q);
+        free(visited);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Exact kNN.  thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:
  *   exact_knn :126-248  - score(q,p) = -<p,q> (mips, :118-120) or squared L2 (:92-100); per query a
  *                         bounded max-heap keeps the k smallest scores (:206-234);

@@ -45,12 +45,12 @@ def capi():
 # without atomics (16-bit entries where the id range allows / 32-bit ids), 0 auto (= 4)
 CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 5, 1, 2),
            (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 4, 3, 1), (2, 1, 4, 3, 3), (2, 2, 5, 3, 3), (2, 4, 4, 0, 0),
-           (2, 8, 0, 3, 3), (2, 2, 4, 3, 3, 1), (2, 4, 2, 3, 3, 2), (1, 3, 3, 3, 1, 2))
+           (2, 8, 0, 3, 3), (2, 2, 4, 3, 3, 1), (2, 4, 2, 3, 3, 2), (1, 3, 3, 3, 1, 2), (2, 2, 4, 3, 3, 3), (2, 5, 2, 3, 3, 3))
 
 
 def configure(ix, cfg, **kw):
     gather, warps, space, l2, pf = cfg[:5]
-    bm = cfg[5] if len(cfg) > 5 else 0   # batch_mode: 0 auto, 1 per-warp gather lists, 2 one list per query
+    bm = cfg[5] if len(cfg) > 5 else 0   # batch_mode: 0 auto, 1 per-warp gather lists, 2 one list per query, 3 per-warp + stealing
     ix.configure(gather=gather, warps_per_query=warps, hash_space=space, l2_hint=l2, adj_prefetch=pf, batch_mode=bm, **kw)
 
 
@@ -103,6 +103,32 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
     ix.close()
 
 
+@pytest.mark.parametrize("metric", (0, 1))
+@pytest.mark.parametrize("warps,space,hash_log2", [(0, 0, 0), (2, 4, 0), (4, 5, 0), (2, 2, 0), (3, 3, 0), (1, 4, 0), (2, 4, 9), (8, 0, 0)])
+def test_build_search_expanded_vs_oracle(capi, oracle, metric, warps, space, hash_log2):
+    """The connectivity-enhancement searches (SearchProjectionGraphInternal, src/index_bipartite.cpp:1279-1350; K1's build
+    variant): expanded nodes of base rows used as queries, in expansion order, ids and distance bit patterns, against the
+    oracle - every visited-set flavour, incl. a table small enough to send queries through the big-table pass."""
+    rng = np.random.default_rng(31 + metric)
+    n, dim = 20000, 64
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    off, adj = random_graph(rng, n, 4, 40, zero_frac=0.01)   # duplicates and self loops included
+    ep = int(np.argmax(np.diff(off)))
+    ix = capi.Index(base, off, adj, ep, metric=metric)
+    ix.configure(warps_per_query=warps, hash_space=space, hash_log2=hash_log2)
+    node_lo, count = 1234, 400
+    for L, cap in ((20, 32), (100, 100), (300, 64)):
+        want_ids, want_d, want_n = oracle.search_expanded(base, off, adj, ep, node_lo, count, L, cap, metric=metric)
+        got_ids, got_d, got_n = ix.search_expanded(node_lo, count, L, cap)
+        assert (got_n == want_n).all(), (L, np.argwhere(got_n != want_n)[:5].ravel(), got_n[:8], want_n[:8])
+        mask = np.arange(cap)[None, :] < want_n[:, None]
+        assert (got_ids[mask] == want_ids[mask]).all(), f"L={L} warps={warps} space={space}"
+        assert (got_d.view(np.uint32)[mask] == want_d.view(np.uint32)[mask]).all(), f"L={L} warps={warps} space={space}"
+    if hash_log2:
+        assert ix.last_overflow > 0
+    ix.close()
+
+
 def test_visited_overflow_takes_exact_fallback(capi, oracle):
     """A tiny visited hash forces most queries through the big-table pass; results stay exact."""
     rng = np.random.default_rng(5)
@@ -141,8 +167,9 @@ def test_hash16_displacement_exhausted(capi, oracle):
 
 def test_bucket16_displacement_exhausted(capi, oracle):
     """Bucketed 16-bit visited set on a 2^20-id range with 128 buckets per query: 13 remainder bits leave 3 displacement bits
-    (6 buckets); the fullest runs exhaust them before the 70 % load limit and those queries take the exact big-table pass.
-    With 1024 buckets nothing overflows.  Eight warps split 128 buckets into 16-bucket ranges (wrap-around probing)."""
+    (a probe window of 7 buckets).  Ids whose window is full go to the per-warp exception list in shared memory (and are
+    found there again); when that list is full too, or the table reaches 90 % load, the query takes the exact big-table pass.
+    With 1024 buckets nothing of the kind happens.  Eight warps split 128 buckets into 16-bucket ranges (wrap-around probing)."""
     rng = np.random.default_rng(12)
     n, dim = 1 << 20, 8
     base = rng.standard_normal((n, dim)).astype(np.float32)
@@ -150,10 +177,15 @@ def test_bucket16_displacement_exhausted(capi, oracle):
     off, adj = random_graph(rng, n, 4, 12)
     ix = capi.Index(base, off, adj, 5, metric=0)
     want = oracle.search(base, off, adj, 5, q, 10, 80, metric=0)
-    for hl, warps, lo, hi in ((10, 2, 1, 300), (10, 8, 1, 300), (13, 2, 0, 0), (13, 1, 0, 0)):
+    seen_exceptions = 0
+    for hl, warps, tight in ((10, 2, True), (10, 8, True), (10, 1, True), (13, 2, False), (13, 1, False)):
         ix.configure(hash_log2=hl, hash_space=4, warps_per_query=warps)
         report(f"bucket16 hl={hl} warps={warps}", ix.search(q, 10, 80), want)
-        assert lo <= ix.last_overflow <= hi, ix.last_overflow
+        if tight:
+            seen_exceptions += ix.last_exceptions
+        else:
+            assert ix.last_overflow == 0 and ix.last_exceptions == 0
+    assert seen_exceptions > 0, "the exception list was never exercised"
     ix.close()
 
 

@@ -60,6 +60,8 @@ def main():
                 ref[L] = key
             same = all(torch.equal(x, y) for x, y in zip(ref[L], key))
             ms = 0.0
+            sampler = bench.ClockSampler(0)  # SM clock under load: a long sweep runs into the power cap
+            sampler.start()
             for _ in range(a.reps):
                 flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -68,14 +70,13 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms += e0.elapsed_time(e1) / a.reps
-            try:  # clock / power state right after the timed repetitions (a long sweep heats the GPU up)
-                smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,temperature.gpu", "--format=csv,noheader,nounits",
-                                      "-i", "0"], capture_output=True, text=True, timeout=10).stdout.strip()
-            except Exception:
-                smi = ""
+            sampler.stop_flag = True
+            sampler.join()
+            clk = sampler.summary()
+            smi = f"{clk['sm_mhz']} MHz {','.join(clk['reasons'])}"
             c = float(cmps.sum().item())
             gbs = c * args.dim * 4 / (ms * 1e-3) / 1e9
-            row = dict(cfg=cfg, L=L, ms=round(ms, 3), qps=round(nq / ms * 1e3), mean_cmps=round(c / nq, 1),
+            row = dict(cfg=cfg, L=L, ms=round(ms, 3), qps=round(nq / ms * 1e3), mean_cmps=round(c / nq, 1), max_cmps=int(cmps.max().item()),
                        gathered_GBs=round(gbs, 1), frac=round(gbs / peak, 4), overflow=ix.last_overflow, same_as_first_cfg=same, smi=smi)
             rows.append(row)
             print(json.dumps(row), flush=True)
