@@ -351,11 +351,43 @@ def time_knn_slice(args, d, rank, world, device):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, same = t[0].item(), int(t[1].item() == 0)
         stats = dict(stats, second_pass_max_rank=int(t[2].item()), exact_scans_max_rank=int(t[3].item()))
-    capi.knn_release_scratch()
-    torch.cuda.empty_cache()
     burst, sustained, kind = load_tensor_peaks()
     nq = q.shape[0]
     flops = 2.0 * nq * args.n * args.dim
+    # Same slice in the grid layout of rg_knn_exact_grid: 2 base shards x N/2 query groups.  The base still is sharded and
+    # the per-shard lists still are exchanged over NCCL and merged, but a shard keeps 1/2 of the rows instead of 1/N, which
+    # keeps K2 in its efficient regime (DESIGN.md "K2").  Reported next to the canonical one-shard-per-GPU figure.
+    grid = None
+    if world >= 4 and world % 2 == 0:
+        (b0, b1), (g0, g1), (o0, o1) = sharded_knn.grid_layout(rank, world, 2, args.n, nq)
+        shard = base[b0:b1]
+
+        def run_grid(qq):
+            (_, _), (h0, h1), _ = sharded_knn.grid_layout(rank, world, 2, args.n, qq.shape[0])
+            return sharded_knn.knn_grid(shard, b0, qq[h0:h1].contiguous(), K, 2, metric=capi.METRIC_IP, stream=st)
+
+        run_grid(q[:min(65536, nq)].contiguous())
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        gids, _ = run_grid(q)
+        e1.record()
+        torch.cuda.synchronize()
+        m = min(512, o1 - o0)
+        want = torch.empty((m, K), dtype=torch.int32, device=device)
+        wd = torch.empty((m, K), dtype=torch.float32, device=device)
+        capi.knn_exact_device(base, q[o0:o0 + m].contiguous(), K, want, wd, metric=capi.METRIC_IP, stream=st)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), float(1 - int(torch.equal(want, gids[:m])))], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = t[0].item()
+        gper = flops / (gms * 1e-3) / 1e12 / world
+        grid = {"layout": f"2 base shards x {world // 2} query groups, rg_knn_exact_grid", "shard_rows": b1 - b0,
+                "knn_s": round(gms * 1e-3, 4), "achieved": round(gper, 1), "frac": round(gper / burst, 4),
+                "c4_extrapolated_s": round(gms * 1e-3 * 10_000_000 / nq * (10_000_000 / args.n), 2),
+                "equals_unsharded": bool(t[1].item() == 0)}
+    capi.knn_release_scratch()
+    torch.cuda.empty_cache()
     per_gpu = flops / (ms * 1e-3) / 1e12 / world
     return {"bound": "tensor", "achieved": round(per_gpu, 1), "peak": burst, "unit": "TFLOP/s per GPU",
             "frac": round(per_gpu / burst, 4), "frac_of_sustained_peak": round(per_gpu / sustained, 4), "peak_kind": kind,
@@ -363,7 +395,8 @@ def time_knn_slice(args, d, rank, world, device):
             "n_ranks": world, "shard_rows": b[1] - b[0], "queries": nq, "K": K, "knn_s": round(ms * 1e-3, 4),
             "algorithmic_flops": flops, "c4_extrapolated_s": round(ms * 1e-3 * 10_000_000 / nq * (10_000_000 / args.n), 2),
             "parallelism": "1 GPU" if world == 1 else f"base sharded over {world} GPUs, rg_knn_exact_sharded (grouped ncclSend/ncclRecv + K4 merge)",
-            "sharded_equals_unsharded": bool(same) if world > 1 else None, "knn_stats": stats}
+            "sharded_equals_unsharded": bool(same) if world > 1 else None, "knn_stats": stats,
+            **({"grid": grid} if grid else {})}
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -173,6 +173,16 @@ RG_API rg_status rg_knn_exact_sharded(const float *d_base_shard, uint64_t n_shar
                                       const float *d_queries, uint64_t nq, uint32_t dim, int metric, uint32_t K,
                                       uint32_t *d_ids, float *d_dists, void *nccl_comm, int rank, int world,
                                       int device, void *cuda_stream);
+/* Grid layout over the same communicator: the `world` ranks form world / base_shards query groups of base_shards ranks each.
+ * Rank r holds base shard r % base_shards (of base_shards shards of the base) and the nq_group queries of group
+ * r / base_shards - only those - and ends up with the merged top-K of slice rg_knn_sharded_slice(nq_group, r % base_shards,
+ * base_shards) of ITS GROUP's queries; the exchange runs between the ranks of one group only.  base_shards == world is the
+ * call above, base_shards == 1 is plain query sharding (whole base on every GPU, no exchange).  The base needs as many
+ * shards as it takes to fit HBM; beyond that, fewer and larger shards keep K2 in its efficient regime (DESIGN.md "K2"). */
+RG_API rg_status rg_knn_exact_grid(const float *d_base_shard, uint64_t n_shard, uint64_t id_base,
+                                   const float *d_group_queries, uint64_t nq_group, uint32_t dim, int metric, uint32_t K,
+                                   uint32_t *d_ids, float *d_dists, void *nccl_comm, int rank, int world, int base_shards,
+                                   int device, void *cuda_stream);
 /* Host-buffer variant (H2D of the shard and the queries, the call above on a private stream, D2H of the slice): ids / dists
  * are host arrays of (hi - lo) x K entries.  Used by the compute_groundtruth driver, one host thread per GPU. */
 RG_API rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, uint64_t id_base,

@@ -23,7 +23,7 @@ SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_i
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_expanded_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count", "rg_search_last_exception_count",
            "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
-           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
+           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_grid", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
            "rg_knn_sharded_slice", "rg_nccl_get_unique_id", "rg_nccl_comm_init_rank", "rg_nccl_comm_init_all",
            "rg_nccl_comm_destroy", "rg_nccl_version"]
 
@@ -90,6 +90,8 @@ def lib():
     L.rg_knn_release_scratch.argtypes = [i32]
     L.rg_knn_exact_sharded.restype = i32
     L.rg_knn_exact_sharded.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32, vp]
+    L.rg_knn_exact_grid.restype = i32
+    L.rg_knn_exact_grid.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32, i32, vp]
     L.rg_knn_exact_sharded_host.restype = i32
     L.rg_knn_exact_sharded_host.argtypes = [vp, u64, u64, vp, u64, u32, i32, u32, vp, vp, vp, i32, i32, i32]
     L.rg_knn_sharded_slice.restype = None
@@ -344,6 +346,16 @@ def nccl_comm_init_rank(world, rank, unique_id: bytes, device):
 
 def nccl_comm_destroy(comm):
     _check(lib().rg_nccl_comm_destroy(comm))
+
+
+def knn_exact_grid(d_base_shard, id_base, d_group_queries, K, d_ids, d_dists, comm, rank, world, base_shards, metric=METRIC_IP,
+                   stream=None):
+    """rg_knn_exact_grid on CUDA torch tensors: rank holds base shard rank % base_shards and the queries of group
+    rank // base_shards; d_ids/d_dists hold slice rank % base_shards of the group's queries."""
+    n, dim = d_base_shard.shape
+    device = d_base_shard.device.index or 0
+    _check(lib().rg_knn_exact_grid(d_base_shard.data_ptr(), n, id_base, d_group_queries.data_ptr(), d_group_queries.shape[0], dim,
+                                   metric, K, d_ids.data_ptr(), d_dists.data_ptr(), comm, rank, world, base_shards, device, stream))
 
 
 def knn_exact_sharded(d_base_shard, id_base, d_queries, K, d_ids, d_dists, comm, rank, world, metric=METRIC_IP, stream=None):

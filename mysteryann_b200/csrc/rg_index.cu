@@ -254,7 +254,7 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         return RG_OK;
     }
     if (!strcmp(name, "l2_hint")) {
-        if (value < 0 || value > 7) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..7");
+        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "l2_hint is a bit mask 0..3");
         ix->cfg_l2_hint = value;
         return RG_OK;
     }

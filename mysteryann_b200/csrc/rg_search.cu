@@ -945,6 +945,8 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     if (want_bucket) {
         // slots wanted: load <= 0.4 at the usual number of visited nodes (auto_hash_log2 rounds this up to a power of two
         // for the atomicCAS tables; the buckets take it as it is)
+        // (target loads of 0.5 / 0.6 - smaller slabs - measured no faster, and 0.6 runs into the load limit:
+        // profiles/r02_k1_table_sizing.txt)
         const double want = ix->cfg_hash_log2 ? double(1u << ix->cfg_hash_log2) : (1000.0 + 30.0 * L) / 0.4;
         const uint32_t nbw = std::max<uint32_t>(uint32_t((want + 7.0) / 8.0), 8u);           // 8 entries per bucket
         const uint32_t min_nb16 = id_bits > 13 ? 1u << (id_bits - 13) : 1u;                   // entry keeps <= 13 bits of x
@@ -1166,23 +1168,9 @@ static rg_status search_device_impl(rg_index *ix, const float *d_queries, uint64
     }
     RG_CUDA_OK(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(uint32_t), st));
     const uint64_t slab_bytes = uint64_t(grid1) * g1.slab_bytes;
-    int max_persist = 0, max_window = 0;
-    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device) != cudaSuccess) {
-        (void)cudaGetLastError();
-        max_persist = max_window = 0;
-    }
     if (g1.slab_bytes && (ix->cfg_l2_hint & 2) && persisting_window_fits(ix, slab_bytes)) {
         // pin the visited-hash slabs of the resident CTAs in the persisting part of L2 (atomics take no cache hint)
-        uint64_t limit = slab_bytes;
-        if (const char *e = std::getenv("RG_K1_PERSIST_SLACK_PCT"))  // experiment: set-aside larger than the window
-            limit = std::min<uint64_t>(uint64_t(max_persist), slab_bytes * (100 + uint64_t(atoi(e))) / 100);
-        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, limit, 1.0f, st);
-        if (s != RG_OK) return s;
-    } else if (g1.slab_bytes && (ix->cfg_l2_hint & 4) && max_persist > 0 && slab_bytes <= uint64_t(max_window)) {
-        // experimental (l2_hint bit 2): slabs larger than the set-aside - pin the fraction that fits
-        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, uint64_t(max_persist),
-                                          float(double(max_persist) / double(slab_bytes)), st);
+        s = launch_with_persisting_window(ix, g1, grid1, ix->d_ghash, slab_bytes, slab_bytes, 1.0f, st);
         if (s != RG_OK) return s;
     } else {
         s = set_persisting_limit(ix, 0);

@@ -177,6 +177,35 @@ def knn_sharded(d_base_shard: torch.Tensor, id_base: int, d_queries: torch.Tenso
     return gather_rows(ids, qb, group), gather_rows(d, qb, group), qb
 
 
+def grid_layout(rank: int, world: int, base_shards: int, n: int, nq: int):
+    """Rows of the base and of the query set rank `rank` works on in the base_shards x (world / base_shards) grid of
+    rg_knn_exact_grid, and the query rows whose merged lists it ends up with:
+    ((base_lo, base_hi), (group_lo, group_hi), (out_lo, out_hi)) - all as global row ranges."""
+    assert base_shards >= 1 and world % base_shards == 0
+    groups = world // base_shards
+    s, g = rank % base_shards, rank // base_shards
+    bb, gb = shard_bounds(n, base_shards), shard_bounds(nq, groups)
+    sb = shard_bounds(gb[g + 1] - gb[g], base_shards)
+    return (bb[s], bb[s + 1]), (gb[g], gb[g + 1]), (gb[g] + sb[s], gb[g] + sb[s + 1])
+
+
+def knn_grid(d_base_shard: torch.Tensor, id_base: int, d_group_queries: torch.Tensor, K: int, base_shards: int, metric: int = 1,
+             group=None, stream: Optional[int] = None):
+    """rg_knn_exact_grid: the ranks form world / base_shards query groups of base_shards ranks; this rank holds base shard
+    rank % base_shards and its group's queries (see grid_layout) and gets (ids, dists) of its slice of the group's queries."""
+    from . import capi
+
+    if not (d_base_shard.is_cuda and d_group_queries.is_cuda):
+        raise capi.RoarGraphError(capi.RG_ERR_NO_DEVICE, "knn_grid needs CUDA tensors (there is no CPU fallback)")
+    comm, rank, world = nccl_comm_for(group, d_base_shard.device.index or 0)
+    sb = shard_bounds(d_group_queries.shape[0], base_shards)
+    mine = sb[rank % base_shards + 1] - sb[rank % base_shards]
+    ids = torch.empty((mine, K), dtype=torch.int32, device=d_group_queries.device)
+    d = torch.empty((mine, K), dtype=torch.float32, device=d_group_queries.device)
+    capi.knn_exact_grid(d_base_shard, id_base, d_group_queries, K, ids, d, comm, rank, world, base_shards, metric=metric, stream=stream)
+    return ids, d
+
+
 def knn_sharded_torch(d_base_shard: torch.Tensor, id_base: int, d_queries: torch.Tensor, K: int, metric: int = 1, group=None,
                       gather: bool = True, stream: Optional[int] = None):
     """The same decomposition with torch.distributed's all-to-all as the exchange (round 1's path; kept as the yardstick

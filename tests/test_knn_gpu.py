@@ -214,3 +214,56 @@ def test_knn_sharded_capi_two_gpus(capi, oracle, seg, monkeypatch):
         lo, hi, ids, d = out[r]
         check_knn(ids, d, want_ids[lo:hi], want_d[lo:hi], f"sharded rank {r}")
         capi.nccl_comm_destroy(C.c_void_p(comms[r]))
+
+
+@pytest.mark.parametrize("world,base_shards", [(2, 1), (2, 2), (4, 2), (4, 1), (4, 4)])
+def test_knn_grid_capi(capi, oracle, world, base_shards):
+    """rg_knn_exact_grid: base_shards base shards x world / base_shards query groups over one communicator (threads, one per
+    GPU).  Every rank holds shard rank % base_shards and ITS group's queries only, the exchange runs inside a group
+    (peer = group * base_shards + p); base_shards = 1 is plain query sharding, base_shards = world the sharded call.
+    Skipped when the box has fewer GPUs than ranks."""
+    import ctypes as C
+    import threading
+
+    import torch
+    from mysteryann_b200 import sharded_knn, synth
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, nq, dim, K = 30011, 1003, 200, 30
+    base, q, _ = synth.make_numpy(n, nq, 1, dim, seed=13)
+    want_ids, want_d, _ = oracle.exact_knn(base, q, K, metric=1)
+    comms = (C.c_void_p * world)()
+    assert capi.lib().rg_nccl_comm_init_all(comms, world, None) == 0, capi.lib().rg_last_error_string()
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            dev = torch.device("cuda", r)
+            with torch.cuda.device(dev):
+                (b0, b1), (g0, g1), (o0, o1) = sharded_knn.grid_layout(r, world, base_shards, n, nq)
+                shard = torch.from_numpy(base[b0:b1]).to(dev)
+                dq = torch.from_numpy(q[g0:g1]).to(dev)
+                ids = torch.empty((o1 - o0, K), dtype=torch.int32, device=dev)
+                d = torch.empty((o1 - o0, K), dtype=torch.float32, device=dev)
+                capi.knn_exact_grid(shard, b0, dq, K, ids, d, C.c_void_p(comms[r]), r, world, base_shards, metric=1)
+                out[r] = (o0, o1, ids.cpu().numpy().view(np.uint32), d.cpu().numpy())
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert err == [None] * world, err
+    covered = np.zeros(nq, bool)
+    for r in range(world):
+        lo, hi, ids, d = out[r]
+        check_knn(ids, d, want_ids[lo:hi], want_d[lo:hi], f"grid {base_shards}x{world // base_shards} rank {r}")
+        assert not covered[lo:hi].any()
+        covered[lo:hi] = True
+        capi.nccl_comm_destroy(C.c_void_p(comms[r]))
+    assert covered.all()
+    with pytest.raises(capi.RoarGraphError):   # base_shards must divide world
+        capi.knn_exact_grid(torch.zeros((8, dim), device="cuda"), 0, torch.zeros((8, dim), device="cuda"), 4,
+                            torch.zeros((8, 4), dtype=torch.int32, device="cuda"), torch.zeros((8, 4), device="cuda"),
+                            None, 0, 4, 3, metric=1)

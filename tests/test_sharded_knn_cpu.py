@@ -101,6 +101,12 @@ def test_grid_layout():
     assert rb == [0, 3, 5, 8, 10]
     with pytest.raises(ValueError):
         sharded_knn.Grid(3, world=8, rank=0)
+    # grid_layout (the row ranges rg_knn_exact_grid works on) agrees with Grid for every rank
+    for world, bs, n, nq in ((8, 2, 1001, 103), (4, 4, 10, 7), (4, 1, 9, 11)):
+        for r in range(world):
+            g = sharded_knn.Grid(bs, world=world, rank=r)
+            rb = g.result_bounds(nq)
+            assert sharded_knn.grid_layout(r, world, bs, n, nq) == (g.base_bounds(n), g.query_bounds(nq), (rb[r], rb[r + 1]))
 
 
 def _grid_worker(rank, world, port, base_shards, n, nq, dim, K, metric, out_dir):

@@ -51,14 +51,18 @@ def main():
     else:
         # base shards x query groups: this rank answers its group's queries against its base shard; the exchange and the
         # merge run inside the group.  `qb` below are the bounds of the merged slices in rank order.
-        grid = sharded_knn.Grid(a.base_shards).make_groups()
+        grid = sharded_knn.Grid(a.base_shards)
+        if a.exchange != "capi":
+            grid.make_groups()
         lo, hi = grid.base_bounds(a.n)
         shard = base[lo:hi]
 
         def run(q=train):
             q0, q1 = grid.query_bounds(q.shape[0])
-            ids, d, _ = knn(shard, lo, q[q0:q1].contiguous(), a.K, metric=capi.METRIC_IP, group=grid.group,
-                                                gather=False, stream=st)
+            if a.exchange == "capi":   # rg_knn_exact_grid: one communicator, the exchange runs inside each query group
+                ids, d = sharded_knn.knn_grid(shard, lo, q[q0:q1].contiguous(), a.K, a.base_shards, metric=capi.METRIC_IP, stream=st)
+            else:
+                ids, d, _ = knn(shard, lo, q[q0:q1].contiguous(), a.K, metric=capi.METRIC_IP, group=grid.group, gather=False, stream=st)
             return ids, d, grid.result_bounds(q.shape[0])
 
     run(train[:min(a.warm, a.nq)].contiguous())  # warm-up (NCCL channels, scratch)
@@ -89,7 +93,7 @@ def main():
                               tflops_per_gpu=round(flops / (ms * 1e-3) / 1e12 / world, 1),
                               c4_extrapolated_s=round(ms * 1e-3 * (10_000_000 / a.nq) * (10_000_000 / a.n), 1),
                               sharded_equals_unsharded=ok, base_shards=a.base_shards or world,
-                              exchange="rg_knn_exact_sharded: grouped ncclSend/ncclRecv + K4 merge" if a.exchange == "capi"
+                              exchange=("rg_knn_exact_sharded" if a.base_shards in (0, world) else "rg_knn_exact_grid") + ": grouped ncclSend/ncclRecv + K4 merge" if a.exchange == "capi"
                               else "torch all_to_all_single + K4 merge", knn_stats=capi.knn_last_stats())), flush=True)
     dist.barrier()
     dist.destroy_process_group()
