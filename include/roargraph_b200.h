@@ -103,7 +103,8 @@ RG_API rg_status rg_search_configure(rg_index *index, int gather, int warps_per_
  * "l2_hint" bit mask (default 3): 1 = gathered base rows are loaded evict_first, 2 = the visited-hash slabs are pinned in
  * the persisting part of L2 (access-policy window; raises the device's persisting-L2 limit); "adj_prefetch" bit mask
  * (default 3): 1 = read the adjacency row of the next unexpanded pool entry ahead and prefetch the visited-hash slots of its
- * neighbours into L2, 2 = L2-prefetch the adjacency rows of scored candidates that beat it;
+ * neighbours into L2, 2 = L2-prefetch the adjacency rows of scored candidates that beat it, 4 (bucketed visited set, off by
+ * default: measured no gain) = when that prediction holds, issue the next hop's visited filter and first gather before the merge;
  * "batch_mode": 0 auto, 1 every warp gathers the unvisited neighbours it filtered itself, 2 the hop's unvisited neighbours go to
  * one list per query and the warps pull batches of stage_rows rows from it, 3 per-warp lists handed out in batches, a warp
  * that has emptied its own takes batches of the others';

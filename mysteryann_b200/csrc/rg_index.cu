@@ -259,7 +259,7 @@ rg_status rg_search_set_option(rg_index *ix, const char *name, int value) {
         return RG_OK;
     }
     if (!strcmp(name, "adj_prefetch")) {
-        if (value < 0 || value > 3) return rg::fail(RG_ERR_INVALID_ARGUMENT, "adj_prefetch is a bit mask 0..3");
+        if (value < 0 || value > 7) return rg::fail(RG_ERR_INVALID_ARGUMENT, "adj_prefetch is a bit mask 0..7");
         ix->cfg_adj_prefetch = value;
         return RG_OK;
     }

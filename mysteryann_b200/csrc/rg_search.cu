@@ -42,6 +42,7 @@ constexpr int kMaxWarps = 8;
 // shared control words
 enum { kCtlWork = 0, kCtlNvis = 1, kCtlHashFull = 2, kCtlHop0 = 4 /* 2 x {ncand, ndup, minlo, curpos} */,
        kCtlFresh = 12 /* ids in the CTA-wide gather list */, kCtlBatch = 13 /* next batch of it */,
+       kCtlBeat0 = 14 /* 2 x: a candidate of the hop beat the node speculated on */,
        kCtlPub0 = 16 /* per warp: 1 + length of its gather list once it is complete */, kCtlNext0 = 24 /* per warp: next batch */ };
 // visited-set flavours
 enum { kHashShared = 0, kHashGlobal32 = 1, kHashGlobal16 = 2, kHashBucket16 = 3, kHashBucket32 = 4 };
@@ -88,6 +89,8 @@ struct SearchParams {
     // node_lo + w, that node is never scored, the entry point is marked visited, and the EXPANDED nodes are recorded
     uint32_t shared_batches;   // 1 = the hop's unvisited ids go to one CTA-wide list and the warps pull batches of stage_rows from it
     uint32_t steal_batches;    // 1 = per-warp lists; a warp that has finished its own takes batches of the others' (no extra barrier)
+    uint32_t early_issue;      // 1 = when the read-ahead prediction holds, filter + first gather of the next hop are issued BEFORE the merge
+    uint32_t early_row0;       // ... into warp 0's staging rows from this one up (the rows below hold the merge scratch)
     uint32_t node_lo, exp_cap;
     uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
     uint32_t *exp_cnt;         // [nq]
@@ -208,7 +211,7 @@ __device__ __forceinline__ void bucket_scan32(const uint4 a, const uint4 b, uint
 // of 7 full buckets is a 1e-8 event per insert at load 0.5, a 10 000-query batch at L_pq = 200 makes 1e8 inserts: the two
 // to six queries per batch that hit it used to be re-run from scratch by the big-table pass after the launch (5-18 % of
 // the batch time).  A later lookup of such an id walks the same full window, ends here too and finds it in the list.
-constexpr uint32_t kExcCap = 15;
+constexpr uint32_t kExcCap = 3;  // 16 bytes per warp with the count; a fourth such id in one query takes the big-table pass
 template <int kHash>
 __device__ __forceinline__ uint32_t bucket_test_and_set(unsigned char *slab, const SearchParams &p, uint32_t blo, uint32_t bhi,
                                                         bool active, uint32_t id, bool have_pre, const uint4 pre, uint32_t lane,
@@ -398,39 +401,76 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
         }
     };
 
+    // bucket flavours: test-and-set of the n_mine ids in s_mine (this warp's share of the expanded row); the unvisited ones
+    // are compacted into s_cid.  from_spec: the list was made a hop ahead and lane l holds the bucket of entry l
+    auto filter_mine = [&](uint32_t n_mine, bool from_spec) -> uint32_t {
+        uint32_t n_w = 0;
+        for (uint32_t r0 = 0; r0 < n_mine; r0 += 32) {
+            const bool act = r0 + lane < n_mine;
+            const uint32_t id = act ? s_mine[r0 + lane] : 0u;
+            const bool pre = RG_K1_SPEC_SECTOR_REGS && kHash == kHashBucket16 && from_spec && r0 == 0;
+            uint32_t v = kBucket ? bucket_test_and_set<kBucket ? kHash : kHashBucket16>(slab, p, blo, bhi, act, id, pre, spec_sec, lane, s_exc) : 0u;
+            if (v == 2u) {
+                s_ctrl[kCtlHashFull] = 1;
+                v = 0;
+            }
+            const bool fresh = v == 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+            if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = id;
+            n_w += __popc(m);
+        }
+        __syncwarp();
+        return n_w;
+    };
+
+    // issues the gather of rows list[0..rows) into this warp's staging rows row0 .. row0 + rows - 1
+    auto issue_rows = [&](const uint32_t *list, uint32_t rows, uint32_t row0) {
+        if (kGather == 2) {
+            if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
+            __syncwarp();
+            if (lane < rows) {  // stage_rows <= 32: one row per lane
+                float *dst = s_stage + (row0 + lane) * RS;
+                const float *src = p.base + size_t(list[lane]) * dim;
+                // the gathered rows are touched once: evict_first keeps them from displacing adjacency/hash lines
+                if (rows_evict_first) bulk_g2s_hint(dst, src, dim * 4u, s_mbar, pol_first);
+                else bulk_g2s(dst, src, dim * 4u, s_mbar);
+            }
+        } else {
+            const uint32_t total = rows * cpr;
+            for (uint32_t idx = lane; idx < total; idx += 32) {
+                const uint32_t r = __umulhi(idx, p.chunk_magic);
+                const uint32_t c = idx - r * cpr;
+                cp_async16(s_stage + size_t(row0 + r) * RS + 4 * c, p.base + size_t(list[r]) * dim + 4 * c);
+            }
+            cp_async_commit();
+        }
+    };
+
     // Gathers and scores the rows s_cid[0..n) (this warp's own list, or its batch of the CTA-wide one); keys below `tail`
-    // are appended to the CTA-wide candidate list.
+    // are appended to the CTA-wide candidate list.  The first `pre` rows may already be on their way (staging rows pre_row0..).
     // Candidates that beat `next_key` (the best unexpanded pool entry besides the node being expanded) are expanded before
-    // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged.
-    auto gather_and_score = [&](const uint32_t *s_cid, uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key, bool do_spec) {
-        for (uint32_t c0 = 0; c0 < n; c0 += BR) {
-            const uint32_t rows = min(BR, n - c0);
-            const float *stage = s_stage;
+    // it: their adjacency rows are prefetched into L2 while the rest of the hop is still being scored and merged, and the
+    // hop is flagged so that the next one does not start from the speculated node.
+    auto gather_and_score = [&](const uint32_t *s_cid, uint32_t n, uint64_t tail, uint32_t ctl, uint64_t next_key, bool do_spec,
+                                uint32_t pre, uint32_t pre_row0) {
+        for (uint32_t c0 = 0; c0 < n;) {
+            uint32_t rows, row0 = 0;
+            if (c0 == 0 && pre) {
+                rows = pre;
+                row0 = pre_row0;
+            } else {
+                rows = min(BR, n - c0);
+                issue_rows(s_cid + c0, rows, 0);
+            }
+            if (do_spec && c0 == 0) spec_block();
             if (kGather == 2) {
-                if (lane == 0) mbar_arrive_expect_tx(s_mbar, rows * dim * 4u);
-                __syncwarp();
-                if (lane < rows) {  // stage_rows <= 32: one row per lane
-                    float *dst = s_stage + lane * RS;
-                    const float *src = p.base + size_t(s_cid[c0 + lane]) * dim;
-                    // the gathered rows are touched once: evict_first keeps them from displacing adjacency/hash lines
-                    if (rows_evict_first) bulk_g2s_hint(dst, src, dim * 4u, s_mbar, pol_first);
-                    else bulk_g2s(dst, src, dim * 4u, s_mbar);
-                }
-                if (do_spec && c0 == 0) spec_block();
                 mbar_wait(s_mbar, mb_phase);
                 mb_phase ^= 1u;
             } else {
-                const uint32_t total = rows * cpr;
-                for (uint32_t idx = lane; idx < total; idx += 32) {
-                    const uint32_t r = __umulhi(idx, p.chunk_magic);
-                    const uint32_t c = idx - r * cpr;
-                    cp_async16(s_stage + size_t(r) * RS + 4 * c, p.base + size_t(s_cid[c0 + r]) * dim + 4 * c);
-                }
-                cp_async_commit();
-                if (do_spec && c0 == 0) spec_block();
                 cp_async_wait<0>();
                 __syncwarp();
             }
+            const float *stage = s_stage + size_t(row0) * RS;
             for (uint32_t r0 = 0; r0 < rows; r0 += 8) {
                 const uint32_t r = r0 + grp;
                 const bool valid = r < rows;
@@ -442,7 +482,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 // NeighborPriorityQueue::insert rejects keys behind the last entry of a full pool (neighbor.h:151);
                 // the tail only tightens during a hop, so dropping them here is exact
                 const bool keep = valid && t == 0 && key < tail;
-                if (pf_cand && keep && key < next_key) bulk_prefetch_l2(p.adj + size_t(s_cid[c0 + rr]) * p.adj_stride, adj_row_bytes);
+                if (keep && key < next_key) {
+                    if (pf_cand) bulk_prefetch_l2(p.adj + size_t(s_cid[c0 + rr]) * p.adj_stride, adj_row_bytes);
+                    s_ctrl[kCtlBeat0 + ((ctl - kCtlHop0) >> 2)] = 1;
+                }
                 const uint32_t m = __ballot_sync(0xffffffffu, keep);
                 if (m) {
                     const uint32_t leader = __ffs(m) - 1;
@@ -453,6 +496,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 }
             }
             __syncwarp();  // all reads of the staging buffer done before the next batch lands in it
+            c0 += rows;
         }
     };
 
@@ -470,10 +514,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             s_ctrl[kCtlHop0 + 5] = 0;
             s_ctrl[kCtlHop0 + 6] = L;
             s_ctrl[kCtlHop0 + 7] = L;
+            s_ctrl[kCtlBeat0] = 0;
+            s_ctrl[kCtlBeat0 + 1] = 0;
             s_ctrl[kCtlFresh] = 0;
             s_ctrl[kCtlBatch] = 0;
         }
-        if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;  // publication words and batch counters of the W <= 8 warps
+        if (p.steal_batches && tid < 16) s_ctrl[kCtlPub0 + tid] = 0;  // publication words and batch counters of the W <= 8 warps
         if (kBucket && lane == 0) s_exc[0] = 0;
         __syncthreads();
         const uint32_t w = s_ctrl[kCtlWork];
@@ -513,7 +559,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 if (kBuild && !kBucket) visit(p.ep);
             }
             __syncwarp();
-            gather_and_score(s_cid, 1, tail, kCtlHop0, ~0ull, false);
+            gather_and_score(s_cid, 1, tail, kCtlHop0, ~0ull, false, 0, 0);
         }
 
         for (;;) {
@@ -525,6 +571,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 overflow = true;
                 break;
             }
+            // Early expansion (bucket flavours): the previous hop read ahead the node it expected to be expanded next - its
+            // neighbours this warp owns are listed in s_mine, their buckets are in registers.  If no candidate of that hop
+            // beat it, it IS the next node and keeps its pool position (every new key lands behind it), so the visited
+            // filter and the first gather are issued now and the rows travel while the CTA merges the candidates.
+            uint32_t n_w = 0, pre_rows = 0;
+            const uint32_t pre_row0 = warp == 0 ? p.early_row0 : 0u;
+            const bool early = kBucket && p.early_issue && have_cur && spec_id != kEmpty && s_ctrl[kCtlBeat0 + hp] == 0 &&
+                               nvis + p.adj_stride <= p.hash_limit;
+            if (early) {
+                n_w = filter_mine(spec_n, true);
+                if (n_w) {
+                    if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
+                    pre_rows = min(BR - pre_row0, n_w);
+                    issue_rows(s_cid, pre_rows, pre_row0);
+                }
+            }
             uint32_t start;
             if (C == 0) {
                 // nothing to insert: flag the expanded entry (closest_unexpanded, neighbor.h:185-192)
@@ -534,10 +596,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[octl + 1] = 0;
                     s_ctrl[octl + 2] = L;
                     s_ctrl[octl + 3] = L;
+                    s_ctrl[kCtlBeat0 + (hp ^ 1u)] = 0;
                     s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
                     s_ctrl[kCtlBatch] = 0;
                 }
-                if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
+                if (p.steal_batches && tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
                 __syncthreads();
                 start = cur + 1;
             } else {
@@ -560,10 +623,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     s_ctrl[octl + 1] = 0;
                     s_ctrl[octl + 2] = L;
                     s_ctrl[octl + 3] = L;
+                    s_ctrl[kCtlBeat0 + (hp ^ 1u)] = 0;
                     s_ctrl[kCtlFresh] = 0;  // every warp has left the previous hop's batch loop
                     s_ctrl[kCtlBatch] = 0;
                 }
-                if (tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
+                if (p.steal_batches && tid < 16) s_ctrl[kCtlPub0 + tid] = 0;
                 __syncthreads();
                 const uint32_t Cn = C - s_ctrl[ctl + 1];   // candidates that are really new
                 const uint32_t minlo = min(s_ctrl[ctl + 2], size);  // pool entries in front of it do not move
@@ -648,34 +712,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
             const uint32_t cur_id = key_id(P[cur]);
             if (kBuild && tid == 0 && hops < p.exp_cap) p.exp_keys[size_t(qi) * p.exp_cap + hops] = P[cur] & ~1ull;  // :1318
             ++hops;
-            if (nvis + p.adj_stride > p.hash_limit) {  // visited set may fill up: hand over to the big-table pass
-                overflow = true;
-                break;
-            }
-            // adjacency row.  CAS flavours: neighbour j is handled by warp j % W, lane (j / W) % 32; bucket flavours: every
-            // warp reads the whole row (word i by lane i % 32) and keeps the neighbours whose home bucket it owns.  The first
-            // three rounds are requested together with the degree word: one DRAM round trip - or none at all when this
-            // node was the one read ahead during the previous hop
-            const uint32_t *row = p.adj + size_t(cur_id) * p.adj_stride;
-            const bool spec_hit = spec_id == cur_id;
-            uint32_t wreg[3], deg;
-            if (spec_hit) {
-#pragma unroll
-                for (uint32_t it = 0; it < 3; ++it) wreg[it] = sreg[it];
-                deg = spec_deg;
-            } else {
-#pragma unroll
-                for (uint32_t it = 0; it < 3; ++it) {
-                    const uint32_t j = kBucket ? lane + 32 * it : (lane + 32 * it) * W + warp;
-                    wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
-                }
-                deg = __ldg(row);
-            }
             // speculation for the NEXT hop: the best unexpanded entry behind `cur` is expanded next unless a candidate of
-            // this hop beats it; read its adjacency row now (same round trip as the row above)
+            // this hop beats it; its adjacency row is read now (same round trip as the row of `cur`, or the first gather)
             uint64_t next_key = tail;
-            spec_id = kEmpty;
-            if (pf_next || pf_cand) {
+            auto spec_scan = [&]() {
+                spec_id = kEmpty;
+                if (!(pf_next || pf_cand)) return;
                 uint32_t c = cur + 1, nx = size;
                 while (c < size) {
                     const uint32_t i = c + lane;
@@ -700,58 +742,71 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                         spec_deg = __ldg(nrow);
                     }
                 }
-            }
-            uint32_t n_w = 0;
-            if (kBucket) {
-                // this warp's neighbours are in s_mine: listed a hop ahead (speculation held) or now
-                const uint32_t n_mine = spec_hit ? spec_n : compact_mine(row, deg, wreg);
-                for (uint32_t r0 = 0; r0 < n_mine; r0 += 32) {
-                    const bool act = r0 + lane < n_mine;
-                    const uint32_t id = act ? s_mine[r0 + lane] : 0u;
-                    const bool pre = RG_K1_SPEC_SECTOR_REGS && kHash == kHashBucket16 && spec_hit && r0 == 0;
-                    uint32_t v = bucket_test_and_set<kHash>(slab, p, blo, bhi, act, id, pre, spec_sec, lane, s_exc);
-                    if (v == 2u) {
-                        s_ctrl[kCtlHashFull] = 1;
-                        v = 0;
-                    }
-                    const bool fresh = v == 1u;
-                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                    if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = id;
-                    n_w += __popc(m);
-                }
+            };
+            if (early) {
+                spec_scan();  // the pool is merged now; the filter and the first rows of this hop are already out
             } else {
-                for (uint32_t it = 0; it * 32 * W < deg; ++it) {
-                    const uint32_t j = (lane + 32 * it) * W + warp;
-                    uint32_t word;
-                    if (it == 0) word = wreg[0];
-                    else if (it == 1) word = wreg[1];
-                    else if (it == 2) word = wreg[2];
-                    else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
-                    uint32_t v = 0;
-                    if (j < deg && !(kBuild && word == self)) v = visit(word);
-                    if (kHash == kHashGlobal16 && v == 2u) {
-                        s_ctrl[kCtlHashFull] = 1;
-                        v = 0;
-                    }
-                    const bool fresh = v == 1u;
-                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                    if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
-                    n_w += __popc(m);
+                if (nvis + p.adj_stride > p.hash_limit) {  // visited set may fill up: hand over to the big-table pass
+                    overflow = true;
+                    break;
                 }
-            }
-            __syncwarp();
-            if (!kBucket && pf_next && spec_id != kEmpty && kHash != kHashShared) {
-                // pull the visited-hash slots the speculated node's neighbours map to into L2: one hop from now their
-                // atomicCAS probes are L2 hits instead of HBM round trips on the query's dependent chain
+                // adjacency row.  CAS flavours: neighbour j is handled by warp j % W, lane (j / W) % 32; bucket flavours:
+                // every warp reads the whole row (word i by lane i % 32) and keeps the neighbours whose home bucket it owns.
+                // The first three rounds are requested together with the degree word: one DRAM round trip - or none at
+                // all when this node was the one read ahead during the previous hop
+                const uint32_t *row = p.adj + size_t(cur_id) * p.adj_stride;
+                const bool spec_hit = spec_id == cur_id;
+                uint32_t wreg[3], deg;
+                if (spec_hit) {
 #pragma unroll
-                for (uint32_t it = 0; it < 3; ++it) {
-                    const uint32_t j = (lane + 32 * it) * W + warp;
-                    if (j < spec_deg) {
-                        if (kHash == kHashGlobal16) {
-                            uint32_t rem;
-                            prefetch_l2(hash16 + hash16_home(p, sreg[it], &rem));
-                        } else {
-                            prefetch_l2(hash32 + ((sreg[it] * 0x9E3779B1u) >> (32 - p.hash_log2)));
+                    for (uint32_t it = 0; it < 3; ++it) wreg[it] = sreg[it];
+                    deg = spec_deg;
+                } else {
+#pragma unroll
+                    for (uint32_t it = 0; it < 3; ++it) {
+                        const uint32_t j = kBucket ? lane + 32 * it : (lane + 32 * it) * W + warp;
+                        wreg[it] = (j + 1 < p.adj_stride) ? __ldg(row + 1 + j) : kEmpty;
+                    }
+                    deg = __ldg(row);
+                }
+                spec_scan();
+                if (kBucket) {
+                    // this warp's neighbours are in s_mine: listed a hop ahead (speculation held) or now
+                    n_w = filter_mine(spec_hit ? spec_n : compact_mine(row, deg, wreg), spec_hit);
+                } else {
+                    for (uint32_t it = 0; it * 32 * W < deg; ++it) {
+                        const uint32_t j = (lane + 32 * it) * W + warp;
+                        uint32_t word;
+                        if (it == 0) word = wreg[0];
+                        else if (it == 1) word = wreg[1];
+                        else if (it == 2) word = wreg[2];
+                        else word = (j < deg) ? __ldg(row + 1 + j) : kEmpty;
+                        uint32_t v = 0;
+                        if (j < deg && !(kBuild && word == self)) v = visit(word);
+                        if (kHash == kHashGlobal16 && v == 2u) {
+                            s_ctrl[kCtlHashFull] = 1;
+                            v = 0;
+                        }
+                        const bool fresh = v == 1u;
+                        const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                        if (fresh) s_cid[n_w + __popc(m & lanemask_lt())] = word;
+                        n_w += __popc(m);
+                    }
+                    __syncwarp();
+                }
+                if (!kBucket && pf_next && spec_id != kEmpty && kHash != kHashShared) {
+                    // pull the visited-hash slots the speculated node's neighbours map to into L2: one hop from now their
+                    // atomicCAS probes are L2 hits instead of HBM round trips on the query's dependent chain
+#pragma unroll
+                    for (uint32_t it = 0; it < 3; ++it) {
+                        const uint32_t j = (lane + 32 * it) * W + warp;
+                        if (j < spec_deg) {
+                            if (kHash == kHashGlobal16) {
+                                uint32_t rem;
+                                prefetch_l2(hash16 + hash16_home(p, sreg[it], &rem));
+                            } else {
+                                prefetch_l2(hash32 + ((sreg[it] * 0x9E3779B1u) >> (32 - p.hash_log2)));
+                            }
                         }
                     }
                 }
@@ -776,7 +831,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                     if (lane == 0) b = atomicAdd(&s_ctrl_nv[kCtlBatch], 1u);
                     b = __shfl_sync(0xffffffffu, b, 0) * BR;
                     if (b >= F) break;
-                    gather_and_score(s_fresh + b, min(BR, F - b), tail, kCtlHop0 + 4 * hp, next_key, first);
+                    gather_and_score(s_fresh + b, min(BR, F - b), tail, kCtlHop0 + 4 * hp, next_key, first, 0, 0);
                     first = false;
                 }
                 if (first) spec_block();
@@ -806,14 +861,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                         if (lane == 0) b = atomicAdd(&s_ctrl_nv[kCtlNext0 + vw], 1u);
                         b = __shfl_sync(0xffffffffu, b, 0) * BR;
                         if (b >= n_v) break;
-                        gather_and_score(list + b, min(BR, n_v - b), tail, kCtlHop0 + 4 * hp, next_key, first);
+                        gather_and_score(list + b, min(BR, n_v - b), tail, kCtlHop0 + 4 * hp, next_key, first, 0, 0);
                         first = false;
                     }
                 }
                 if (first) spec_block();
             } else if (n_w) {
-                if (lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
-                gather_and_score(s_cid, n_w, tail, kCtlHop0 + 4 * hp, next_key, true);
+                if (!early && lane == 0) atomicAdd(&s_ctrl_nv[kCtlNvis], n_w);
+                gather_and_score(s_cid, n_w, tail, kCtlHop0 + 4 * hp, next_key, true, pre_rows, pre_row0);
             } else {
                 spec_block();
             }
@@ -928,7 +983,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     uint32_t hl = ix->cfg_hash_log2 ? uint32_t(ix->cfg_hash_log2) : auto_hash_log2(L, build || space != 1);
     p.fallback = fallback ? 1u : 0u;
     p.l2_hint = uint32_t(ix->cfg_l2_hint);
-    p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch);
+    p.adj_prefetch = uint32_t(ix->cfg_adj_prefetch) & 3u;
     const int batch_mode = ix->cfg_batch_mode;
     // visited set: a slab per CTA in global memory unless shared memory was asked for (hash_space 1).
     //   hash_space 0 (auto) / 4: buckets without atomics - 16-bit quotient entries (8 per 16-byte bucket) when the id range
@@ -999,6 +1054,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     // one CTA-wide gather list with dynamic batches: measured no better than per-warp lists (profiles/r02_k1_sweep_buckets.txt), opt-in
     p.shared_batches = batch_mode == 2 && W > 1 ? 1u : 0u;
     p.steal_batches = batch_mode == 3 && W > 1 ? 1u : 0u;
+    p.early_issue = bucket && (ix->cfg_adj_prefetch & 1) && (ix->cfg_adj_prefetch & 4) && !p.shared_batches && !p.steal_batches ? 1u : 0u;
 
     // Shared-memory layout, packed to 16 bytes (TMA bulk destinations and LDS.128 need no more): the CTA count per SM is
     // decided by it (12 CTAs of two warps fit up to L_pq ~ 170 at D = 200, 11 at 500).  The merge scratch (sorted candidates
@@ -1009,7 +1065,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.off_cand = off;
     off += round_up(ix->adj_stride * 8, 16);
     p.off_ctrl = off;
-    off += 128;
+    off += p.steal_batches ? 128 : 64;  // words 16..31 are the stealing mode's publication words and batch counters
     p.off_fresh = off;
     if (p.shared_batches) off += round_up(ix->adj_stride * 4, 16);
     p.off_hash = off;
@@ -1021,10 +1077,16 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     p.woff_mine = p.woff_cid + cid_cap * 4;
     p.woff_exc = p.woff_mine + (bucket ? cid_cap * 4 : 0);
     p.woff_stage = round_up(p.woff_exc + (bucket ? (kExcCap + 1) * 4 : 0), 16);
-    const uint32_t stage_bytes = std::max<uint32_t>(round_up(p.stage_rows * p.row_stride * 4, 16),
+    // the padding behind the last staged row is not needed
+    const uint32_t stage_bytes = std::max<uint32_t>(round_up(((p.stage_rows - 1) * p.row_stride + ix->dim) * 4, 16),
                                                     round_up(ix->adj_stride * 8, 16) + round_up(ix->adj_stride * 4, 16));
     p.warp_bytes = p.woff_stage + stage_bytes;
     p.off_sorted = p.off_warp + p.woff_stage;                       // aliases warp 0's staging rows
+    {   // early issue: warp 0's first rows land above the merge scratch
+        const uint32_t scratch = round_up(ix->adj_stride * 8, 16) + round_up(ix->adj_stride * 4, 16);
+        p.early_row0 = (scratch + p.row_stride * 4 - 1) / (p.row_stride * 4);
+        if (p.early_row0 >= p.stage_rows) p.early_issue = 0;
+    }
     p.off_pos = p.off_sorted + round_up(ix->adj_stride * 8, 16);
     off += W * p.warp_bytes;
     g->smem_bytes = off;

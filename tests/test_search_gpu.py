@@ -40,12 +40,13 @@ def capi():
 
 
 # (gather, warps per query, visited-hash space, L2 hints, adjacency prefetch): cp.async / TMA bulk gathers, 1..8 warps per
-# query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch
+# query, shared / global hash, evict_first rows + persisting hash window, speculative adjacency prefetch (bit 2 = 4: early
+# issue of the next hop's filter and first gather before the merge)
 # hash space: 1 shared memory, 2 / 3 global atomicCAS tables (32-bit keys / 16-bit quotient entries), 4 / 5 global buckets
 # without atomics (16-bit entries where the id range allows / 32-bit ids), 0 auto (= 4)
 CONFIGS = ((2, 4, 2, 0, 0), (1, 4, 3, 0, 0), (2, 1, 1, 0, 0), (2, 2, 3, 3, 3), (1, 3, 1, 3, 3), (2, 8, 5, 1, 2),
            (2, 2, 0, 2, 1), (2, 2, 2, 0, 0), (2, 3, 4, 3, 1), (2, 1, 4, 3, 3), (2, 2, 5, 3, 3), (2, 4, 4, 0, 0),
-           (2, 8, 0, 3, 3), (2, 2, 4, 3, 3, 1), (2, 4, 2, 3, 3, 2), (1, 3, 3, 3, 1, 2), (2, 2, 4, 3, 3, 3), (2, 5, 2, 3, 3, 3))
+           (2, 8, 0, 3, 3), (2, 2, 4, 3, 3, 1), (2, 4, 2, 3, 3, 2), (1, 3, 3, 3, 1, 2), (2, 2, 4, 3, 3, 3), (2, 5, 2, 3, 3, 3), (2, 2, 4, 3, 7), (2, 3, 5, 3, 5), (2, 8, 4, 0, 7), (2, 1, 4, 3, 7), (2, 4, 0, 3, 7))
 
 
 def configure(ix, cfg, **kw):
@@ -104,8 +105,9 @@ def test_random_graph_vs_oracle(capi, oracle, metric, dim, dmin, dmax):
 
 
 @pytest.mark.parametrize("metric", (0, 1))
-@pytest.mark.parametrize("warps,space,hash_log2", [(0, 0, 0), (2, 4, 0), (4, 5, 0), (2, 2, 0), (3, 3, 0), (1, 4, 0), (2, 4, 9), (8, 0, 0)])
-def test_build_search_expanded_vs_oracle(capi, oracle, metric, warps, space, hash_log2):
+@pytest.mark.parametrize("warps,space,hash_log2,pf", [(0, 0, 0, 3), (2, 4, 0, 3), (4, 5, 0, 3), (2, 2, 0, 3), (3, 3, 0, 3), (1, 4, 0, 3),
+                                                      (2, 4, 9, 3), (8, 0, 0, 3), (2, 4, 0, 7), (3, 5, 0, 7), (2, 4, 9, 7)])
+def test_build_search_expanded_vs_oracle(capi, oracle, metric, warps, space, hash_log2, pf):
     """The connectivity-enhancement searches (SearchProjectionGraphInternal, src/index_bipartite.cpp:1279-1350; K1's build
     variant): expanded nodes of base rows used as queries, in expansion order, ids and distance bit patterns, against the
     oracle - every visited-set flavour, incl. a table small enough to send queries through the big-table pass."""
@@ -115,7 +117,7 @@ def test_build_search_expanded_vs_oracle(capi, oracle, metric, warps, space, has
     off, adj = random_graph(rng, n, 4, 40, zero_frac=0.01)   # duplicates and self loops included
     ep = int(np.argmax(np.diff(off)))
     ix = capi.Index(base, off, adj, ep, metric=metric)
-    ix.configure(warps_per_query=warps, hash_space=space, hash_log2=hash_log2)
+    ix.configure(warps_per_query=warps, hash_space=space, hash_log2=hash_log2, adj_prefetch=pf)
     node_lo, count = 1234, 400
     for L, cap in ((20, 32), (100, 100), (300, 64)):
         want_ids, want_d, want_n = oracle.search_expanded(base, off, adj, ep, node_lo, count, L, cap, metric=metric)
