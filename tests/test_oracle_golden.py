@@ -72,6 +72,38 @@ def test_knn_matches_fp64(oracle, metric):
     assert np.mean([len(g & set(r)) / 20 for g, r in zip(got_set, ref_ids)]) > 0.999
 
 
+@pytest.mark.parametrize("metric", (0, 1))
+def test_build_search_restatement(oracle, metric):
+    """rgo_search_projection_internal (SearchProjectionGraphInternal, src/index_bipartite.cpp:1279-1350) against the pinned
+    search restatement: for a target row that nobody links to, the two beam searches differ only in that the build search
+    marks the entry point visited (:1311), which cannot change the pool (a re-scored entry point is dropped as a duplicate,
+    neighbor.h:161) - so the number of expanded nodes equals the hops of rgo_search_roargraph with that row as the query,
+    the first expanded node is the entry point, no node is expanded twice and the target never shows up."""
+    rng = np.random.default_rng(41 + metric)
+    n, dim, L = 3000, 24, 40
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    deg = rng.integers(3, 14, n)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=off[1:])
+    node_lo, count = 100, 60
+    adj = rng.integers(0, n - count, int(off[-1])).astype(np.uint32)
+    adj[adj >= node_lo] += count                    # nobody links to the targets [node_lo, node_lo + count)
+    ep = 7
+    ids, dists, cnt = oracle.search_expanded(base, off, adj, ep, node_lo, count, L, 4 * L, metric=metric)
+    ref = oracle.search(base, off, adj, ep, base[node_lo:node_lo + count], 10, L, metric=metric, threads=2)
+    assert (cnt == ref["hops"]).all()
+    assert (ids[:, 0] == ep).all()
+    for t in range(count):
+        row = ids[t, :cnt[t]]
+        assert len(set(row.tolist())) == len(row) and node_lo + t not in row
+        assert dists[t, 0] == oracle.distance_batch(metric, base[ep:ep + 1], base[node_lo + t:node_lo + t + 1])[0]
+    # a target that IS linked is skipped as a neighbour (:1328): it is never expanded either
+    adj2 = adj.copy()
+    adj2[off[ep]:off[ep + 1]] = node_lo
+    ids2, _, cnt2 = oracle.search_expanded(base, off, adj2, ep, node_lo, 1, L, 4 * L, metric=metric)
+    assert node_lo not in ids2[0, :cnt2[0]] and cnt2[0] == 1   # the entry point's only neighbour is the target itself
+
+
 def test_recall(oracle):
     gt = np.array([[1, 2, 3, 9], [4, 5, 6, 9]], np.uint32)
     res = np.array([[3, 1, 7], [8, 8, 8]], np.uint32)
