@@ -330,12 +330,24 @@ def time_knn_slice(args, d, rank, world, device):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    ids, _ = run(q)
-    e1.record()
-    torch.cuda.synchronize()
+    # best of three repetitions: on the shared boxes of this pool a single repetition occasionally takes 1.5-2x (host-side
+    # hiccups between the ~100 launches of a call); every repetition is listed in the line
+    reps_ms = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        ids, _ = run(q)
+        e1.record()
+        torch.cuda.synchronize()
+        r_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([r_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # a repetition takes as long as its slowest rank
+            r_ms = t.item()
+        reps_ms.append(r_ms)
     stats = capi.knn_last_stats()
-    ms = e0.elapsed_time(e1)
+    ms = min(reps_ms)
     # the merged slices must equal the unsharded kernels' answer (first rows of this rank's slice)
     same = 1
     if world > 1:
@@ -349,7 +361,7 @@ def time_knn_slice(args, d, rank, world, device):
         t = torch.tensor([ms, float(1 - same), float(stats["second_pass"]), float(stats["exact_scans"])], device=device,
                          dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, same = t[0].item(), int(t[1].item() == 0)
+        same = int(t[1].item() == 0)
         stats = dict(stats, second_pass_max_rank=int(t[2].item()), exact_scans_max_rank=int(t[3].item()))
     burst, sustained, kind = load_tensor_peaks()
     nq = q.shape[0]
@@ -368,22 +380,27 @@ def time_knn_slice(args, d, rank, world, device):
 
         run_grid(q[:min(65536, nq)].contiguous())
         torch.cuda.synchronize()
-        dist.barrier()
-        e0.record()
-        gids, _ = run_grid(q)
-        e1.record()
-        torch.cuda.synchronize()
+        g_reps = []
+        for _ in range(3):
+            dist.barrier()
+            e0.record()
+            gids, _ = run_grid(q)
+            e1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            g_reps.append(tt.item())
         m = min(512, o1 - o0)
         want = torch.empty((m, K), dtype=torch.int32, device=device)
         wd = torch.empty((m, K), dtype=torch.float32, device=device)
         capi.knn_exact_device(base, q[o0:o0 + m].contiguous(), K, want, wd, metric=capi.METRIC_IP, stream=st)
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1), float(1 - int(torch.equal(want, gids[:m])))], device=device, dtype=torch.float64)
+        t = torch.tensor([0.0, float(1 - int(torch.equal(want, gids[:m])))], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gms = t[0].item()
+        gms = min(g_reps)
         gper = flops / (gms * 1e-3) / 1e12 / world
         grid = {"layout": f"2 base shards x {world // 2} query groups, rg_knn_exact_grid", "shard_rows": b1 - b0,
-                "knn_s": round(gms * 1e-3, 4), "achieved": round(gper, 1), "frac": round(gper / burst, 4),
+                "knn_s": round(gms * 1e-3, 4), "repetitions_s": [round(x * 1e-3, 4) for x in g_reps], "achieved": round(gper, 1), "frac": round(gper / burst, 4),
                 "c4_extrapolated_s": round(gms * 1e-3 * 10_000_000 / nq * (10_000_000 / args.n), 2),
                 "equals_unsharded": bool(t[1].item() == 0)}
     capi.knn_release_scratch()
@@ -393,6 +410,7 @@ def time_knn_slice(args, d, rank, world, device):
             "frac": round(per_gpu / burst, 4), "frac_of_sustained_peak": round(per_gpu / sustained, 4), "peak_kind": kind,
             "kernel": "knn_gemm_filter_kernel (tcgen05 kind::f16) + select + FP32 re-rank" + (" + NCCL exchange + K4 merge" if world > 1 else ""),
             "n_ranks": world, "shard_rows": b[1] - b[0], "queries": nq, "K": K, "knn_s": round(ms * 1e-3, 4),
+            "timing": "best of 3 repetitions, CUDA events, max over ranks per repetition", "repetitions_s": [round(x * 1e-3, 4) for x in reps_ms],
             "algorithmic_flops": flops, "c4_extrapolated_s": round(ms * 1e-3 * 10_000_000 / nq * (10_000_000 / args.n), 2),
             "parallelism": "1 GPU" if world == 1 else f"base sharded over {world} GPUs, rg_knn_exact_sharded (grouped ncclSend/ncclRecv + K4 merge)",
             "sharded_equals_unsharded": bool(same) if world > 1 else None, "knn_stats": stats,

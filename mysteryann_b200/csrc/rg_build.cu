@@ -834,6 +834,7 @@ rg_status rg_index_create_from_graph(rg_index **out, const float *d_base, uint64
     if (e == cudaSuccess) e = cudaMemcpy(ix->d_adj, g->d_adj, n * uint64_t(g->stride) * sizeof(uint32_t), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&ix->d_counters, 64 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ix->d_counters, 0, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) ix->reserve_search_scratch();
     if (e != cudaSuccess) {
         rg_index_destroy(ix);
         return rg::fail(e == cudaErrorMemoryAllocation ? RG_ERR_OUT_OF_MEMORY : RG_ERR_CUDA, "rg_index_create_from_graph: %s",

@@ -146,6 +146,7 @@ rg_status rg_index_create(rg_index **out, const float *base, uint64_t n, uint32_
     if (e != cudaSuccess) return cleanup_fail(rg::fail(RG_ERR_CUDA, "adjacency upload failed: %s", cudaGetErrorString(e)));
     RG_TRY(cudaMalloc(&ix->d_counters, 64 * sizeof(uint32_t)));
     RG_TRY(cudaMemset(ix->d_counters, 0, 64 * sizeof(uint32_t)));
+    ix->reserve_search_scratch();
 #undef RG_TRY
     *out = ix;
     return RG_OK;

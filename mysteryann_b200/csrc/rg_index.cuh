@@ -46,6 +46,16 @@ struct rg_index {
     int cfg_batch_mode = 0;  // 0 auto, 1 every warp gathers the unvisited neighbours it filtered, 2 one CTA-wide list, batches pulled dynamically
     int cfg_zero_copy = 1;  // rg_search_batch: search straight out of / into page-locked caller buffers
 
+    // Visited-set scratch is taken once, large enough for every beam width of the reference's sweep (210 MB at L_pq = 500 on
+    // 148 SMs): growing it inside a search call costs a cudaFree + cudaMalloc in the middle of an L_pq sweep (measured: the
+    // single timed call per L_pq of the drop-in driver lost 2 ms at every growth step).  Best effort - K1 sizes it exactly
+    // if this allocation is not there.
+    void reserve_search_scratch() {
+        const uint64_t bytes = 256ull << 20;
+        if (!d_ghash && cudaMalloc(&d_ghash, bytes) == cudaSuccess) ghash_words = bytes / 4;
+        else (void)cudaGetLastError();
+    }
+
     uint64_t persist_bytes = 0;  // persisting-L2 set-aside requested so far (l2_hint bit 1)
     uint64_t launches = 0;
 };
