@@ -190,6 +190,11 @@ RG_API rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_s
                                            const float *queries, uint64_t nq, uint32_t dim, int metric, uint32_t K,
                                            uint32_t *ids, float *dists, void *nccl_comm, int rank, int world,
                                            int device);
+/* ... and of rg_knn_exact_grid: `queries` are the nq queries of the caller's group, ids / dists receive slice
+ * rg_knn_sharded_slice(nq, rank % base_shards, base_shards) of them (compute_groundtruth --devices N --base_shards B). */
+RG_API rg_status rg_knn_exact_grid_host(const float *base_shard, uint64_t n_shard, uint64_t id_base, const float *group_queries,
+                                        uint64_t nq_group, uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists,
+                                        void *nccl_comm, int rank, int world, int base_shards, int device);
 /* Query rows [*lo, *hi) whose merged lists rank `rank` of `world` receives (contiguous, ascending with the rank; the first
  * nq % world slices hold one extra row). */
 RG_API void rg_knn_sharded_slice(uint64_t nq, int rank, int world, uint64_t *lo, uint64_t *hi);

@@ -23,7 +23,7 @@ SYMBOLS = ["rg_last_error_string", "rg_version_string", "rg_device_count", "rg_i
            "rg_index_info", "rg_search_batch", "rg_search_batch_device", "rg_search_expanded_device", "rg_search_configure", "rg_search_set_option", "rg_search_last_overflow_count", "rg_search_last_exception_count",
            "rg_host_register", "rg_host_unregister", "rg_index_launch_count", "rg_knn_exact", "rg_knn_exact_device", "rg_knn_merge_device", "rg_knn_merge",
            "rg_knn_last_stats", "rg_build_roargraph_device", "rg_build_roargraph", "rg_graph_info", "rg_graph_download", "rg_graph_destroy",
-           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_grid", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
+           "rg_index_create_from_graph", "rg_knn_last_second_pass_count", "rg_knn_release_scratch", "rg_knn_exact_sharded", "rg_knn_exact_grid", "rg_knn_exact_grid_host", "rg_knn_exact_sharded_host", "rg_build_projection_lists_device",
            "rg_knn_sharded_slice", "rg_nccl_get_unique_id", "rg_nccl_comm_init_rank", "rg_nccl_comm_init_all",
            "rg_nccl_comm_destroy", "rg_nccl_version"]
 

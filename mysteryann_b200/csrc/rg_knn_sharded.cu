@@ -315,17 +315,19 @@ rg_status rg_knn_exact_grid(const float *d_base_shard, uint64_t n_shard, uint64_
 }
 
 // Host-buffer variant (what the compute_groundtruth driver calls from one thread per GPU): uploads the shard and the
-// queries, runs rg_knn_exact_sharded on a private stream, downloads this rank's slice of merged lists.
-rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, uint64_t id_base, const float *queries,
-                                    uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists,
-                                    void *nccl_comm, int rank, int world, int device) {
+// queries, runs the sharded / grid call on a private stream, downloads this rank's slice of merged lists.  `queries` are the
+// rank's group's queries (all queries when base_shards == world).
+rg_status rg_knn_exact_grid_host(const float *base_shard, uint64_t n_shard, uint64_t id_base, const float *queries,
+                                 uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists,
+                                 void *nccl_comm, int rank, int world, int base_shards, int device) {
     if (!base_shard || !queries || !ids || !dists) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact_sharded_host: null argument");
-    if (world <= 0 || rank < 0 || rank >= world) return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact_sharded_host: bad rank/world");
+    if (world <= 0 || rank < 0 || rank >= world || base_shards <= 0 || world % base_shards != 0)
+        return rg::fail(RG_ERR_INVALID_ARGUMENT, "rg_knn_exact_sharded_host: bad rank/world/base_shards");
     if (rg_device_count() <= 0) return rg::fail(RG_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
     rg::DeviceGuard guard(device);
     if (!guard.ok) return rg::fail(RG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     uint64_t lo = 0, hi = 0;
-    rg_knn_sharded_slice(nq, rank, world, &lo, &hi);
+    rg_knn_sharded_slice(nq, rank % base_shards, base_shards, &lo, &hi);
     struct Bufs {
         float *base = nullptr, *q = nullptr, *d = nullptr;
         uint32_t *i = nullptr;
@@ -345,12 +347,20 @@ rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, u
     RG_CUDA_OK(cudaMalloc(&b.d, std::max<uint64_t>(hi - lo, 1) * K * sizeof(float)));
     RG_CUDA_OK(cudaMemcpyAsync(b.base, base_shard, n_shard * dim * sizeof(float), cudaMemcpyHostToDevice, b.st));
     RG_CUDA_OK(cudaMemcpyAsync(b.q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, b.st));
-    rg_status s = rg_knn_exact_sharded(b.base, n_shard, id_base, b.q, nq, dim, metric, K, b.i, b.d, nccl_comm, rank, world, device, b.st);
+    rg_status s = rg_knn_exact_grid(b.base, n_shard, id_base, b.q, nq, dim, metric, K, b.i, b.d, nccl_comm, rank, world, base_shards,
+                                    device, b.st);
     if (s != RG_OK) return s;
     RG_CUDA_OK(cudaMemcpyAsync(ids, b.i, (hi - lo) * K * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.st));
     RG_CUDA_OK(cudaMemcpyAsync(dists, b.d, (hi - lo) * K * sizeof(float), cudaMemcpyDeviceToHost, b.st));
     RG_CUDA_OK(cudaStreamSynchronize(b.st));
     return RG_OK;
+}
+
+rg_status rg_knn_exact_sharded_host(const float *base_shard, uint64_t n_shard, uint64_t id_base, const float *queries,
+                                    uint64_t nq, uint32_t dim, int metric, uint32_t K, uint32_t *ids, float *dists,
+                                    void *nccl_comm, int rank, int world, int device) {
+    return rg_knn_exact_grid_host(base_shard, n_shard, id_base, queries, nq, dim, metric, K, ids, dists, nccl_comm, rank, world, world,
+                                  device);
 }
 
 }  // extern "C"

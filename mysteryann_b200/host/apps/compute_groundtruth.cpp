@@ -102,7 +102,7 @@ void check(rg_status s, const char *what) {
 
 template <typename T>
 int aux_main(const std::string &base_file, const std::string &query_file, const std::string &gt_file, uint64_t k, int metric,
-             bool cosine, const std::string &tags_file, int n_devices, uint64_t part_rows, bool explicit_parts) {
+             bool cosine, const std::string &tags_file, int n_devices, uint64_t part_rows, bool explicit_parts, int base_shards) {
     const BinHeader bh = read_header(base_file), qh = read_header(query_file);
     std::cout << "Reading bin file " << base_file << " ...\n#pts = " << bh.npts << ", #dims = " << bh.ndims << std::endl;
     if (bh.ndims != qh.ndims) throw std::runtime_error("base and query dimensions differ");
@@ -142,28 +142,35 @@ int aux_main(const std::string &base_file, const std::string &query_file, const 
     // Several GPUs, default part size, no tags: ONE base shard per GPU and the merge on the devices (rg_knn_exact_sharded:
     // K2/K3 per shard, grouped ncclSend/ncclRecv exchange of the per-shard lists over NVLink, K4) instead of the
     // part-by-part walk with a host-side merge below.  One host thread per GPU, communicators from ncclCommInitAll.
-    const bool sharded = n_devices > 1 && location_to_tag.empty() && !explicit_parts && bh.npts >= uint64_t(n_devices) &&
-                         uint64_t(n_devices) * k <= 1024 && (bh.npts / n_devices + 1) * dpad * sizeof(float) <= (64ull << 30);
+    // --base_shards B (default: one shard per GPU) arranges the GPUs as B base shards x devices / B query groups
+    // (rg_knn_exact_grid): fewer, larger shards keep the GEMM in its efficient regime when the base fits B GPUs.
+    const int B = (base_shards > 0 && n_devices % base_shards == 0) ? base_shards : n_devices;
+    const int G = n_devices / B;
+    const bool sharded = n_devices > 1 && location_to_tag.empty() && !explicit_parts && bh.npts >= uint64_t(B) &&
+                         nqueries >= uint64_t(G) && uint64_t(B) * k <= 1024 &&
+                         (bh.npts / B + 1) * dpad * sizeof(float) <= (64ull << 30);
     if (sharded) {
         std::vector<void *> comms(size_t(n_devices), nullptr);
         check(rg_nccl_comm_init_all(comms.data(), n_devices, nullptr), "rg_nccl_comm_init_all");
-        std::cout << "Base sharded over " << n_devices << " GPUs, per-shard lists exchanged with NCCL " << rg_nccl_version()
-                  << " and merged on the devices" << std::endl;
+        std::cout << "Base sharded over " << B << " GPUs x " << G << " query group(s), per-shard lists exchanged with NCCL "
+                  << rg_nccl_version() << " and merged on the devices" << std::endl;
         std::mutex err_mu;
         std::string err;
         auto worker = [&](int dev) {
             try {
-                const uint64_t q = bh.npts / n_devices, r = bh.npts % n_devices;
-                const uint64_t start_id = uint64_t(dev) * q + std::min<uint64_t>(dev, r), npoints = q + (uint64_t(dev) < r ? 1 : 0);
+                const uint64_t shard = uint64_t(dev % B), group = uint64_t(dev / B);
+                const uint64_t q = bh.npts / B, r = bh.npts % B;
+                const uint64_t start_id = shard * q + std::min<uint64_t>(shard, r), npoints = q + (shard < r ? 1 : 0);
                 std::vector<float> base;
                 load_part_as_float<T>(base_file, start_id, npoints, ndims, dpad, base);
                 if (cosine) normalize_rows(base, npoints, ndims, dpad);
-                uint64_t lo = 0, hi = 0;
-                rg_knn_sharded_slice(nqueries, dev, n_devices, &lo, &hi);
-                check(rg_knn_exact_sharded_host(base.data(), npoints, start_id, queries.data(), nqueries, uint32_t(dpad), metric,
-                                                uint32_t(k), closest_points.data() + lo * k, dist_closest_points.data() + lo * k,
-                                                comms[size_t(dev)], dev, n_devices, dev),
-                      "rg_knn_exact_sharded_host");
+                uint64_t g0 = 0, g1 = 0, lo = 0, hi = 0;
+                rg_knn_sharded_slice(nqueries, int(group), G, &g0, &g1);          // this group's queries
+                rg_knn_sharded_slice(g1 - g0, int(shard), B, &lo, &hi);           // the slice of them this GPU ends up with
+                check(rg_knn_exact_grid_host(base.data(), npoints, start_id, queries.data() + g0 * dpad, g1 - g0, uint32_t(dpad),
+                                             metric, uint32_t(k), closest_points.data() + (g0 + lo) * k,
+                                             dist_closest_points.data() + (g0 + lo) * k, comms[size_t(dev)], dev, n_devices, B, dev),
+                      "rg_knn_exact_grid_host");
             } catch (const std::exception &ex) {
                 std::lock_guard<std::mutex> lock(err_mu);
                 if (err.empty()) err = ex.what();
@@ -262,13 +269,13 @@ int aux_main(const std::string &base_file, const std::string &query_file, const 
 int main(int argc, char **argv) {
     std::string data_type, dist_fn, base_file, query_file, gt_file, tags_file;
     uint64_t K = 0, part_rows = kPartSize;
-    int devices = 0;
+    int devices = 0, base_shards = 0;
     bool explicit_parts = false;
     try {
         CliArgs args(argc, argv, {{"-h", "--help"}});
         if (args.has("help")) {
             std::cout << "Arguments:\n  --data_type <int8/uint8/float>\n  --dist_fn <l2/mips/cosine>\n  --base_file F\n  --query_file F\n"
-                         "  --gt_file F\n  --K N\n  [--tags_file F]\n  [--devices N (default: all visible GPUs)] [--part_size rows]\n";
+                         "  --gt_file F\n  --K N\n  [--tags_file F]\n  [--devices N (default: all visible GPUs)] [--base_shards B (default N)] [--part_size rows]\n";
             return 0;
         }
         data_type = args.get<std::string>("data_type");
@@ -279,6 +286,7 @@ int main(int argc, char **argv) {
         K = args.get<uint64_t>("K");
         tags_file = args.get<std::string>("tags_file", std::string());
         devices = args.get<int>("devices", 0);
+        base_shards = args.get<int>("base_shards", 0);
         part_rows = args.get<uint64_t>("part_size", kPartSize);
         explicit_parts = args.has("part_size");
     } catch (const std::exception &ex) {
@@ -316,9 +324,9 @@ int main(int argc, char **argv) {
     try {
         auto t0 = std::chrono::steady_clock::now();
         int rc;
-        if (data_type == "float") rc = aux_main<float>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
-        else if (data_type == "int8") rc = aux_main<int8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
-        else rc = aux_main<uint8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts);
+        if (data_type == "float") rc = aux_main<float>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts, base_shards);
+        else if (data_type == "int8") rc = aux_main<int8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts, base_shards);
+        else rc = aux_main<uint8_t>(base_file, query_file, gt_file, K, metric, cosine, tags_file, devices, part_rows, explicit_parts, base_shards);
         std::cout << "Total time: " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;
         return rc;
     } catch (const std::exception &e) {

@@ -73,10 +73,19 @@ def test_compute_groundtruth_two_gpus_nccl(bins, oracle, tmp_path):
     out = run([os.path.join(bins, "compute_groundtruth"), "--data_type", "float", "--dist_fn", "l2", "--base_file",
                str(tmp_path / "base.fbin"), "--query_file", str(tmp_path / "q.fbin"), "--gt_file", str(tmp_path / "gt.bin"),
                "--K", "25", "--devices", "2"])
-    assert "Base sharded over 2 GPUs" in out
+    assert "Base sharded over 2 GPUs x 1 query group" in out
     ids, dists = io.read_ibin(tmp_path / "gt.bin")
     want_ids, want_d, _ = oracle.exact_knn(base, q, 25, metric=0)
     check_knn(ids, dists, want_ids, want_d, "cli 2 gpus")
+    # grid layouts (rg_knn_exact_grid_host): base shards x query groups over the same communicator
+    layouts = [(2, 1)] + ([(4, 2), (4, 1), (4, 4)] if torch.cuda.device_count() >= 4 else [])
+    for ndev, bs in layouts:
+        out = run([os.path.join(bins, "compute_groundtruth"), "--data_type", "float", "--dist_fn", "l2", "--base_file",
+                   str(tmp_path / "base.fbin"), "--query_file", str(tmp_path / "q.fbin"), "--gt_file", str(tmp_path / "gt2.bin"),
+                   "--K", "25", "--devices", str(ndev), "--base_shards", str(bs)])
+        assert f"Base sharded over {bs} GPUs x {ndev // bs} query group" in out
+        ids, dists = io.read_ibin(tmp_path / "gt2.bin")
+        check_knn(ids, dists, want_ids, want_d, f"cli {ndev} gpus, {bs} base shards")
 
 
 def test_compute_groundtruth_cosine_and_uint8(bins, tmp_path):
