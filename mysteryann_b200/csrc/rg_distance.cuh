@@ -74,4 +74,62 @@ __device__ __forceinline__ float lane_exact_distance(const float4 *__restrict__ 
     return finish_distance<kIP>(acc, tail8, vt, qt, t);
 }
 
+// ---- the same with packed FP32 (sm_100 FFMA2 / FADD2: two IEEE-rounded operations per instruction) -------------------
+// The reference's main loop rounds the product and the sum separately, and ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into one FFMA2 (it does not for the scalar forms), so the product is written as fma(a, b, -0.0): RN(a*b + (-0)) ==
+// RN(a*b) for every input including signed zeros, and the -0.0 pair `nz` comes from the kernel parameters, where the
+// compiler cannot see its value and therefore cannot simplify the fma back into a multiply.  Elementwise the operations
+// and their order are those of main_step / fused_step, so the result is bit-identical.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+constexpr uint64_t kNegZero2 = 0x8000000080000000ull;  // host side: SearchParams::neg_zero2
+
+template <bool kIP>
+__device__ __forceinline__ float lane_exact_distance_x2(const float4 *__restrict__ rp, const float4 *__restrict__ qp,
+                                                         uint32_t n16, bool tail8, uint32_t t, uint64_t nz) {
+    uint64_t a01 = 0, a23 = 0;  // (+0, +0)
+#pragma unroll 4
+    for (uint32_t s = 0; s < n16; ++s) {
+        const float4 v = rp[4 * s], q = qp[4 * s];
+        if (kIP) {
+            a01 = add2(a01, fma2(pack2(v.x, v.y), pack2(q.x, q.y), nz));
+            a23 = add2(a23, fma2(pack2(v.z, v.w), pack2(q.z, q.w), nz));
+        } else {
+            const uint64_t d01 = sub2(pack2(v.x, v.y), pack2(q.x, q.y)), d23 = sub2(pack2(v.z, v.w), pack2(q.z, q.w));
+            a01 = add2(a01, fma2(d01, d01, nz));
+            a23 = add2(a23, fma2(d23, d23, nz));
+        }
+    }
+    float4 acc;
+    unpack2(a01, acc.x, acc.y);
+    unpack2(a23, acc.z, acc.w);
+    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), qt = vt;
+    if (tail8 && t < 2) {
+        vt = rp[4 * n16];
+        qt = qp[4 * n16];
+    }
+    return finish_distance<kIP>(acc, tail8, vt, qt, t);
+}
+
 }  // namespace rg

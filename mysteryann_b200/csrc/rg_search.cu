@@ -92,6 +92,7 @@ struct SearchParams {
     uint32_t early_issue;      // 1 = when the read-ahead prediction holds, filter + first gather of the next hop are issued BEFORE the merge
     uint32_t early_row0;       // ... into warp 0's staging rows from this one up (the rows below hold the merge scratch)
     uint32_t node_lo, exp_cap;
+    uint64_t neg_zero2;        // (-0.0f, -0.0f): addend of the packed product in lane_exact_distance_x2 (opaque to the compiler)
     uint64_t *exp_keys;        // [nq][exp_cap] (distance,id) keys in expansion order
     uint32_t *exp_cnt;         // [nq]
     // byte offsets inside the CTA's shared memory
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 const uint32_t rr = valid ? r : rows - 1;
                 const float4 *rp = reinterpret_cast<const float4 *>(stage + size_t(rr) * RS) + t;
                 const float4 *qp = reinterpret_cast<const float4 *>(s_query) + t;
-                const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
+                const float d = lane_exact_distance_x2<kIP>(rp, qp, n16, tail8, t, p.neg_zero2);
                 const uint64_t key = make_key(d, s_cid[c0 + rr]);
                 // NeighborPriorityQueue::insert rejects keys behind the last entry of a full pool (neighbor.h:151);
                 // the tail only tightens during a hop, so dropping them here is exact
@@ -646,31 +647,41 @@ __global__ void __launch_bounds__(kMaxWarps * 32, RG_K1_MIN_CTAS) rg_search_kern
                 }
                 __syncthreads();
                 // (c) pool entries [minlo, size) shift right by the number of candidates in front of them, in place, in
-                //     chunks of 4T entries (four per thread, independent of each other) from the top down; a chunk's new
-                //     positions are >= its old ones, i.e. inside the chunk itself (read before the barrier) or above it
-                //     (already moved).  Candidate r stands in front of pool entry i iff its pool position s_pos[r] - r is
-                //     <= i (keys are distinct), so the shift is a binary search over 32-bit words
+                //     chunks of 4T entries from the top down; a chunk's new positions are >= its old ones, i.e. inside the
+                //     chunk itself (read before the barrier) or above it (already moved).  Candidate r stands in front of
+                //     pool entry i iff its pool position q_r = s_pos[r] - r is <= i (keys are distinct), so the shift of
+                //     entry i is a binary search over 32-bit words.  A thread moves two PAIRS of neighbouring entries
+                //     (i, i+1): the second shift is the first plus the candidates with q_r == i + 1, one search per pair.
                 for (uint32_t hi = size; hi > minlo;) {
                     const uint32_t lo_c = (hi - minlo > 4 * T) ? hi - 4 * T : minlo;
                     uint64_t e[4];
                     uint32_t pos[4];
 #pragma unroll
-                    for (uint32_t u = 0; u < 4; ++u) {
-                        const uint32_t i = lo_c + tid + u * T;
-                        pos[u] = L;
-                        e[u] = 0;
+                    for (uint32_t u = 0; u < 2; ++u) {
+                        const uint32_t i = lo_c + 2 * (tid + u * T);
+                        pos[2 * u] = pos[2 * u + 1] = L;
+                        e[2 * u] = e[2 * u + 1] = 0;
                         if (i < hi) {
-                            e[u] = P[i];
+                            e[2 * u] = P[i];
                             uint32_t a = 0, b = Cn;
                             while (a < b) {
                                 const uint32_t mid = (a + b) >> 1;
                                 if (s_pos[mid] - mid <= i) a = mid + 1;
                                 else b = mid;
                             }
-                            pos[u] = i + a;
+                            pos[2 * u] = i + a;
+                            if (i + 1 < hi) {
+                                e[2 * u + 1] = P[i + 1];
+                                while (a < Cn && s_pos[a] - a <= i + 1) ++a;
+                                pos[2 * u + 1] = i + 1 + a;
+                            }
                             if (have_cur && i == cur) {
-                                e[u] |= 1ull;
-                                s_ctrl[ctl + 3] = pos[u];
+                                e[2 * u] |= 1ull;
+                                s_ctrl[ctl + 3] = pos[2 * u];
+                            }
+                            if (have_cur && i + 1 == cur && i + 1 < hi) {
+                                e[2 * u + 1] |= 1ull;
+                                s_ctrl[ctl + 3] = pos[2 * u + 1];
                             }
                         }
                     }
@@ -963,6 +974,7 @@ static rg_status make_geometry(const rg_index *ix, uint32_t k, uint32_t L, bool 
     SearchParams &p = g->p;
     const int space = space_override >= 0 ? space_override : ix->cfg_hash_space;
     memset(&p, 0, sizeof(p));
+    p.neg_zero2 = kNegZero2;
     p.dim = ix->dim;
     p.adj_stride = ix->adj_stride;
     p.ep = ix->ep;

@@ -10,6 +10,7 @@ import json
 import os
 import subprocess
 import sys
+import zlib
 
 import torch
 
@@ -77,7 +78,8 @@ def main():
             c = float(cmps.sum().item())
             gbs = c * args.dim * 4 / (ms * 1e-3) / 1e9
             row = dict(cfg=cfg, L=L, ms=round(ms, 3), qps=round(nq / ms * 1e3), mean_cmps=round(c / nq, 1), max_cmps=int(cmps.max().item()),
-                       gathered_GBs=round(gbs, 1), frac=round(gbs / peak, 4), overflow=ix.last_overflow, same_as_first_cfg=same, smi=smi)
+                       gathered_GBs=round(gbs, 1), frac=round(gbs / peak, 4), overflow=ix.last_overflow, same_as_first_cfg=same, smi=smi,
+                       crc=zlib.crc32(key[0].numpy().tobytes() + key[1].numpy().tobytes() + key[2].numpy().tobytes()))  # compare across A/B libraries
             rows.append(row)
             print(json.dumps(row), flush=True)
     if a.out:
