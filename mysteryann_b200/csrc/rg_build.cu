@@ -72,6 +72,7 @@ struct PruneParams {
     const uint32_t *exp_cnt;
     uint32_t exp_cap;
     uint32_t off_R, off_stage, off_keys, off_orig, off_kept, off_mbar;
+    uint64_t neg_zero2;       // (-0.0f, -0.0f) for lane_exact_distance_x2 (rg_distance.cuh), opaque to the compiler
 };
 
 // bijection on 32-bit ids: pairs sort by scrambled source, so a truncated candidate list is a pseudo-random subset
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(32) prune_kernel(const PruneParams p) {
             const bool valid = grp < rows;
             const float4 *rp = reinterpret_cast<const float4 *>(s_stage + size_t(valid ? grp : 0) * RS) + t;
             const float4 *qp = reinterpret_cast<const float4 *>(s_owner) + t;
-            const float d = lane_exact_distance<kIP>(rp, qp, n16, tail8, t);
+            const float d = lane_exact_distance_x2<kIP>(rp, qp, n16, tail8, t, p.neg_zero2);
             if (valid && t == 0) {
                 const uint32_t id = s_orig[b0 + grp];
                 s_keys[b0 + grp] = (id == owner) ? ~0ull : make_key(d, id);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(32) prune_kernel(const PruneParams p) {
                     const bool valid = r < nkept;
                     const float4 *ap = reinterpret_cast<const float4 *>(s_stage + size_t(c) * RS) + t;
                     const float4 *bp = reinterpret_cast<const float4 *>(s_R + size_t(valid ? r : 0) * RS) + t;
-                    const float d = lane_exact_distance<kIP>(ap, bp, n16, tail8, t);
+                    const float d = lane_exact_distance_x2<kIP>(ap, bp, n16, tail8, t, p.neg_zero2);
                     occluded = __any_sync(0xffffffffu, valid && t == 0 && d < pd);
                 }
                 if (!occluded && id != owner) {
@@ -507,6 +508,7 @@ rg_status build_device(const float *d_base, uint64_t n, uint32_t dim, int metric
     // prune kernel geometry
     PruneParams pp;
     memset(&pp, 0, sizeof(pp));
+    pp.neg_zero2 = kNegZero2;
     pp.base = d_base;
     pp.n = n;
     pp.dim = dim;
