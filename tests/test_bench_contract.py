@@ -52,10 +52,5 @@ def test_canonical_configs(monkeypatch):
 
 def test_l_sweep_is_the_references():
     # run_roargraph_search_test.sh:13 of the reference, cut at 500
-    Ls = bench.L_SWEEP if hasattr(bench, "L_SWEEP") else None
-    if Ls is None:
-        for v in vars(bench).values():
-            if isinstance(v, (list, tuple)) and len(v) > 20 and all(isinstance(x, int) for x in v) and v[-1] == 500:
-                Ls = v
-                break
-    assert Ls is not None and list(Ls) == sorted(Ls) and Ls[0] == 10 and Ls[-1] == 500 and 55 in Ls
+    Ls = bench.L_SWEEP
+    assert list(Ls) == sorted(Ls) and Ls[0] == 10 and Ls[-1] == 500 and 55 in Ls
